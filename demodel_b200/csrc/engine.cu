@@ -1,0 +1,1414 @@
+// The blob hash-and-cache engine behind include/demodel_b200.h.
+//
+// Data path:
+//
+//   dm_stream_write ──memcpy──▶ pinned ring slab ──one H2D DMA per slab──▶ the blob's
+//   (many threads)              (per stream)        (copy streams)         CAS extent in HBM
+//                                                                               │
+//   pump thread: every cycle gathers all streams with unhashed bytes into one   ▼
+//   job table and launches ONE multi-buffer SHA-256 kernel over them      sha256_{wide,deep}
+//   (hash stream, ordered after the DMAs by an event); finished streams   (reads each byte once)
+//   get their digest through mapped pinned memory, are compared with the
+//   expected oid and published in the CAS index; the spill thread writes
+//   published blobs to the on-disk tier with D2H copies on a side stream.
+//
+// The bytes land at their final CAS address straight from the DMA, so the
+// ring path costs HBM one write (DMA) + one read (hash) per blob byte.  The
+// device-resident path (dm_ingest_device) fuses the copy into the hash kernel.
+//
+// Reference hooks served: cmd/demodel/start.go:201-204 (ingest) and
+// start.go:197-200 (hit serving); see include/demodel_b200.h.
+#include "../../include/demodel_b200.h"
+#include "sha256_kernels.cuh"
+#include "blobgen.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *what)
+{
+    g_last_error = what ? what : "";
+    return code;
+}
+int fail_cuda(cudaError_t err, const char *where)
+{
+    g_last_error = std::string(where) + ": " + cudaGetErrorString(err);
+    return DM_ECUDA;
+}
+#define CU_TRY(expr)                                                   \
+    do {                                                               \
+        cudaError_t cu_err_ = (expr);                                  \
+        if (cu_err_ != cudaSuccess) return fail_cuda(cu_err_, #expr);  \
+    } while (0)
+
+constexpr uint64_t kAlign = 256;           // CAS extent granularity
+constexpr uint64_t kMaxGrow = 256ull << 20;
+constexpr int kCycles = 4;                 // pump launches in flight
+constexpr int kCopyStreams = 2;
+constexpr size_t kBounceBytes = 4u << 20;
+constexpr int kBounces = 8;
+
+inline uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+struct Digest {
+    uint8_t b[32];
+    bool operator==(const Digest &o) const { return memcmp(b, o.b, 32) == 0; }
+};
+struct DigestHash {
+    size_t operator()(const Digest &d) const
+    {
+        uint64_t v;
+        memcpy(&v, d.b, 8);   // SHA-256 output is already uniform
+        return (size_t)v;
+    }
+};
+
+void words_to_digest(const uint32_t *w, uint8_t out[32])
+{
+    for (int i = 0; i < 8; ++i) {
+        out[4 * i] = (uint8_t)(w[i] >> 24); out[4 * i + 1] = (uint8_t)(w[i] >> 16);
+        out[4 * i + 2] = (uint8_t)(w[i] >> 8); out[4 * i + 3] = (uint8_t)w[i];
+    }
+}
+
+std::string hex_of(const uint8_t *d, size_t n)
+{
+    static const char *hx = "0123456789abcdef";
+    std::string s(2 * n, '0');
+    for (size_t i = 0; i < n; ++i) { s[2 * i] = hx[d[i] >> 4]; s[2 * i + 1] = hx[d[i] & 15]; }
+    return s;
+}
+
+struct Extent { uint64_t off, len; };      // byte range of the HBM arena
+
+// First-fit free list over the HBM arena, coalescing on free.
+class Arena {
+public:
+    void reset(uint64_t bytes) { free_.clear(); if (bytes) free_[0] = bytes; cap_ = bytes; used_ = 0; }
+    bool alloc(uint64_t len, uint64_t *off)
+    {
+        for (auto it = free_.begin(); it != free_.end(); ++it) {
+            if (it->second >= len) {
+                *off = it->first;
+                const uint64_t rest = it->second - len, at = it->first + len;
+                free_.erase(it);
+                if (rest) free_[at] = rest;
+                used_ += len;
+                return true;
+            }
+        }
+        return false;
+    }
+    void release(uint64_t off, uint64_t len)
+    {
+        if (!len) return;
+        used_ -= len;
+        auto nx = free_.lower_bound(off);
+        if (nx != free_.begin()) {
+            auto pv = std::prev(nx);
+            if (pv->first + pv->second == off) { off = pv->first; len += pv->second; free_.erase(pv); }
+        }
+        if (nx != free_.end() && off + len == nx->first) { len += nx->second; free_.erase(nx); }
+        free_[off] = len;
+    }
+    uint64_t used() const { return used_; }
+    uint64_t capacity() const { return cap_; }
+private:
+    std::map<uint64_t, uint64_t> free_;
+    uint64_t cap_ = 0, used_ = 0;
+};
+
+struct Blob {
+    Digest digest;
+    uint64_t size = 0;
+    std::vector<Extent> extents;          // empty once evicted from HBM
+    uint32_t readers = 0;
+    uint64_t tick = 0;
+    bool in_hbm = false;
+    bool on_disk = false;
+    bool spill_done = false;
+};
+
+struct Slab { uint8_t *host; };
+
+enum class St { Open, Finishing, Done, Aborted };
+
+struct Stream {
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t id = 0;
+    uint32_t slot = 0;
+    bool has_expect = false;
+    Digest expect{};
+    std::vector<Extent> extents;
+    uint64_t capacity = 0;     // sum of extents
+    uint64_t received = 0;     // bytes accepted
+    uint64_t dma_issued = 0;   // bytes whose H2D is enqueued (== received - cur_fill)
+    uint64_t hash_issued = 0;  // bytes covered by launched jobs
+    Slab *cur = nullptr;
+    uint32_t cur_fill = 0;
+    bool window_out = false;   // acquire() window outstanding
+    bool dirty = false;        // queued for the pump
+    bool final_issued = false;
+    uint32_t jobs_inflight = 0;
+    St st = St::Open;
+    Digest digest{};
+    int matched = 0;
+    int result = DM_OK;
+    std::shared_ptr<Blob> blob;   // set at commit
+};
+
+struct Reader {
+    std::shared_ptr<Blob> blob;
+    int fd = -1;                  // disk tier
+    uint64_t size = 0;
+};
+
+struct Cycle {
+    bool busy = false;
+    cudaEvent_t copy_ev[kCopyStreams]{};
+    cudaEvent_t k_start{}, k_end{};
+    dm::HashJob *h_jobs = nullptr;   // pinned
+    dm::HashJob *d_jobs = nullptr;
+    uint32_t njobs = 0;
+    bool deep = false;
+    uint64_t bytes = 0;
+    bool slabs_released = false;
+    std::vector<Slab *> slabs;
+    std::vector<std::shared_ptr<Stream>> streams;   // one entry per job
+    std::vector<uint8_t> is_final;
+};
+
+struct Bounce { uint8_t *host = nullptr; cudaStream_t stream{}; };
+
+}  // namespace
+
+struct dm_engine {
+    dm_config cfg{};
+    std::string cas_dir;
+    int device = 0;
+    int sm_count = 148;
+
+    cudaStream_t copy_stream[kCopyStreams]{};
+    cudaStream_t hash_stream{}, ingest_stream{}, util_stream{};
+
+    uint8_t *arena_base = nullptr;
+    std::mutex arena_mu;
+    Arena arena;
+
+    uint8_t *ring = nullptr;
+    std::vector<Slab> slab_store;
+    std::mutex slab_mu;
+    std::condition_variable slab_cv;
+    std::vector<Slab *> slab_free;
+
+    uint32_t *d_states = nullptr;
+    uint32_t *h_digests = nullptr;   // mapped pinned, [max_streams][8]
+    uint32_t *d_digests = nullptr;   // device alias of h_digests
+
+    std::mutex mu;                   // streams / blobs / readers / slots
+    std::unordered_map<uint64_t, std::shared_ptr<Stream>> streams;
+    std::vector<uint32_t> free_slots;
+    uint64_t next_id = 1;
+    std::unordered_map<Digest, std::shared_ptr<Blob>, DigestHash> blobs;
+    std::unordered_map<uint64_t, std::shared_ptr<Reader>> readers;
+    uint64_t tick = 0;
+
+    std::mutex work_mu;              // pump inbox
+    std::condition_variable work_cv;
+    std::vector<std::shared_ptr<Stream>> dirty;
+    std::vector<Slab *> pending_slabs;
+    bool stop = false;
+    std::thread pump;
+    Cycle cycles[kCycles];
+    uint32_t max_jobs = 0;
+
+    std::mutex spill_mu;
+    std::condition_variable spill_cv, spill_done_cv;
+    std::deque<std::shared_ptr<Blob>> spill_q;
+    std::thread spiller;
+
+    std::mutex bounce_mu;
+    std::condition_variable bounce_cv;
+    std::vector<Bounce *> bounce_free;
+    std::vector<Bounce> bounce_store;
+
+    std::mutex ingest_mu;            // dm_ingest_device scratch
+    uint32_t *ing_states = nullptr;
+    uint32_t *ing_digests = nullptr;       // device
+    dm::HashJob *ing_jobs_h = nullptr;     // pinned
+    dm::HashJob *ing_jobs_d = nullptr;
+    uint32_t *ing_digests_h = nullptr;     // pinned
+    uint32_t ing_cap = 0;
+    cudaEvent_t ing_ev0{}, ing_ev1{};
+
+    // stats
+    std::atomic<uint64_t> st_ingested{0}, st_hashed{0}, st_served{0}, st_committed{0}, st_mismatch{0};
+    std::atomic<uint64_t> st_launches{0}, st_wide{0}, st_deep{0}, st_h2d{0}, st_d2h{0};
+    std::mutex stat_mu;
+    double st_kernel_ms = 0.0;
+};
+
+namespace {
+
+// ---- extents ---------------------------------------------------------------
+
+// Visit the device segments covering [off, off+len) of a blob laid out over `ext`.
+template <class F>
+void for_segments(dm_engine *e, const std::vector<Extent> &ext, uint64_t off, uint64_t len, F &&fn)
+{
+    uint64_t base = 0;
+    for (const Extent &x : ext) {
+        if (len == 0) break;
+        if (off < base + x.len) {
+            const uint64_t in = off - base;
+            const uint64_t n = std::min(len, x.len - in);
+            fn(e->arena_base + x.off + in, n);
+            off += n; len -= n;
+        }
+        base += x.len;
+    }
+}
+
+// Device pointer of byte `off`, and how many bytes are contiguous from there.
+uint8_t *seg_at(dm_engine *e, const std::vector<Extent> &ext, uint64_t off, uint64_t *contig)
+{
+    uint64_t base = 0;
+    for (const Extent &x : ext) {
+        if (off < base + x.len) { *contig = base + x.len - off; return e->arena_base + x.off + (off - base); }
+        base += x.len;
+    }
+    *contig = 0;
+    return nullptr;
+}
+
+void free_extents(dm_engine *e, std::vector<Extent> &ext)
+{
+    std::lock_guard<std::mutex> g(e->arena_mu);
+    for (const Extent &x : ext) e->arena.release(x.off, x.len);
+    ext.clear();
+}
+
+// Evict least-recently-used unreferenced blobs until `need` bytes could fit.
+// Caller holds neither e->mu nor arena_mu.
+bool evict_for(dm_engine *e, uint64_t need)
+{
+    for (;;) {
+        std::shared_ptr<Blob> victim;
+        {
+            std::lock_guard<std::mutex> g(e->mu);
+            for (auto &kv : e->blobs) {
+                Blob *b = kv.second.get();
+                if (!b->in_hbm || b->readers) continue;
+                if (!e->cas_dir.empty() && !b->spill_done) continue;   // not yet safe on disk
+                if (!victim || b->tick < victim->tick) victim = kv.second;
+            }
+            if (!victim) return false;
+            victim->in_hbm = false;
+            if (!victim->on_disk) e->blobs.erase(victim->digest);
+        }
+        uint64_t freed = 0;
+        for (const Extent &x : victim->extents) freed += x.len;
+        free_extents(e, victim->extents);
+        std::lock_guard<std::mutex> g(e->arena_mu);
+        uint64_t off;
+        if (e->arena.alloc(need, &off)) { e->arena.release(off, need); return true; }
+        (void)freed;
+    }
+}
+
+bool arena_alloc(dm_engine *e, uint64_t len, Extent *out)
+{
+    len = round_up(std::max<uint64_t>(len, 1), kAlign);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        {
+            std::lock_guard<std::mutex> g(e->arena_mu);
+            uint64_t off;
+            if (e->arena.alloc(len, &off)) { out->off = off; out->len = len; return true; }
+        }
+        if (attempt == 0 && !evict_for(e, len)) return false;
+    }
+    return false;
+}
+
+// Make sure the stream's extents cover `need` bytes.  Stream mutex held.
+int ensure_capacity(dm_engine *e, Stream *s, uint64_t need)
+{
+    while (s->capacity < need) {
+        uint64_t want = need - s->capacity;
+        if (!s->extents.empty()) {   // unknown / exceeded size: grow geometrically
+            const uint64_t grow = std::min<uint64_t>(std::max<uint64_t>(s->capacity, e->cfg.slab_bytes), kMaxGrow);
+            want = std::max(want, grow);
+        }
+        Extent x;
+        if (!arena_alloc(e, want, &x)) {
+            if (!arena_alloc(e, need - s->capacity, &x)) return fail(DM_ENOMEM, "HBM CAS arena exhausted");
+        }
+        s->extents.push_back(x);
+        s->capacity += x.len;
+    }
+    return DM_OK;
+}
+
+// ---- ring slabs --------------------------------------------------------------
+
+Slab *slab_get(dm_engine *e)
+{
+    std::unique_lock<std::mutex> g(e->slab_mu);
+    e->slab_cv.wait(g, [&] { return !e->slab_free.empty() || e->stop; });
+    if (e->slab_free.empty()) return nullptr;
+    Slab *s = e->slab_free.back();
+    e->slab_free.pop_back();
+    return s;
+}
+
+void slab_put(dm_engine *e, Slab *s)
+{
+    {
+        std::lock_guard<std::mutex> g(e->slab_mu);
+        e->slab_free.push_back(s);
+    }
+    e->slab_cv.notify_one();
+}
+
+// Give the stream a fresh slab.  The stream mutex is dropped while waiting for
+// ring back-pressure: the pump needs it to build jobs, and only the pump's
+// reaping frees slabs.
+int take_slab(dm_engine *e, Stream *s, std::unique_lock<std::mutex> &g)
+{
+    g.unlock();
+    Slab *fresh = slab_get(e);
+    g.lock();
+    if (!fresh) return fail(DM_ESTATE, "engine stopping");
+    if (s->st != St::Open) { slab_put(e, fresh); return fail(DM_ESTATE, "stream closed while waiting for the ring"); }
+    if (s->cur) { slab_put(e, fresh); return DM_OK; }
+    s->cur = fresh;
+    s->cur_fill = 0;
+    return DM_OK;
+}
+
+void mark_dirty(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *submitted)
+{
+    {
+        std::lock_guard<std::mutex> g(e->work_mu);
+        if (submitted) e->pending_slabs.push_back(submitted);
+        if (!sp->dirty) { sp->dirty = true; e->dirty.push_back(sp); }
+    }
+    e->work_cv.notify_one();
+}
+
+// DMA the stream's current slab to its place in the blob.  Stream mutex held.
+int submit_slab(dm_engine *e, const std::shared_ptr<Stream> &sp)
+{
+    Stream *s = sp.get();
+    if (!s->cur) return DM_OK;
+    Slab *slab = s->cur;
+    const uint32_t n = s->cur_fill;
+    s->cur = nullptr; s->cur_fill = 0;
+    if (n == 0) { slab_put(e, slab); return DM_OK; }
+    int rc = ensure_capacity(e, s, s->dma_issued + n);
+    if (rc != DM_OK) { slab_put(e, slab); return rc; }
+    cudaStream_t cs = e->copy_stream[s->id % kCopyStreams];
+    const uint8_t *src = slab->host;
+    cudaError_t err = cudaSuccess;
+    for_segments(e, s->extents, s->dma_issued, n, [&](uint8_t *dev, uint64_t len) {
+        if (err == cudaSuccess) err = cudaMemcpyAsync(dev, src, len, cudaMemcpyHostToDevice, cs);
+        src += len;
+    });
+    if (err != cudaSuccess) { slab_put(e, slab); return fail_cuda(err, "cudaMemcpyAsync(H2D slab)"); }
+    s->dma_issued += n;
+    e->st_h2d += n;
+    mark_dirty(e, sp, slab);
+    return DM_OK;
+}
+
+// ---- CAS commit --------------------------------------------------------------
+
+void write_sidecar(const std::string &path, const Blob &b)
+{
+    FILE *f = fopen(path.c_str(), "w");
+    if (!f) return;
+    fprintf(f, "{\"digest\":\"sha256:%s\",\"size\":%llu,\"encoding\":\"identity\",\"engine\":\"demodel_b200\",\"abi\":%u}\n",
+            hex_of(b.digest.b, 32).c_str(), (unsigned long long)b.size, DM_ABI_VERSION);
+    fclose(f);
+}
+
+std::string blob_path(const dm_engine *e, const uint8_t d[32])
+{
+    const std::string hx = hex_of(d, 32);
+    return e->cas_dir + "/blobs/sha256/" + hx.substr(0, 2) + "/" + hx;
+}
+
+// Publish a verified blob.  Returns the blob that now owns the digest (an
+// earlier copy wins; the new extents are then released).
+std::shared_ptr<Blob> publish(dm_engine *e, const Digest &d, uint64_t size, std::vector<Extent> &ext)
+{
+    // trim the last extent to the bytes actually held
+    uint64_t keep = round_up(std::max<uint64_t>(size, 1), kAlign), base = 0;
+    std::vector<Extent> kept;
+    {
+        std::lock_guard<std::mutex> g(e->arena_mu);
+        for (Extent &x : ext) {
+            if (base >= keep) { e->arena.release(x.off, x.len); }
+            else if (base + x.len > keep) {
+                const uint64_t k = keep - base;
+                e->arena.release(x.off + k, x.len - k);
+                kept.push_back({x.off, k});
+            } else kept.push_back(x);
+            base += x.len;
+        }
+    }
+    ext.clear();
+    std::shared_ptr<Blob> b;
+    bool fresh = false;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        auto it = e->blobs.find(d);
+        if (it != e->blobs.end() && it->second->in_hbm) {
+            b = it->second;
+            b->tick = ++e->tick;
+        } else if (it != e->blobs.end()) {   // known on disk only: re-home into HBM
+            b = it->second;
+            b->extents = kept; kept.clear();
+            b->in_hbm = true; b->tick = ++e->tick;
+        } else {
+            b = std::make_shared<Blob>();
+            b->digest = d; b->size = size; b->extents = kept; kept.clear();
+            b->in_hbm = true; b->tick = ++e->tick;
+            e->blobs[d] = b;
+            fresh = true;
+        }
+    }
+    if (!kept.empty()) free_extents(e, kept);
+    e->st_committed++;
+    if (fresh && !e->cas_dir.empty()) {
+        {
+            std::lock_guard<std::mutex> g(e->spill_mu);
+            e->spill_q.push_back(b);
+        }
+        e->spill_cv.notify_one();
+    }
+    return b;
+}
+
+// ---- pump ----------------------------------------------------------------------
+
+void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint32_t *words)
+{
+    Stream *s = sp.get();
+    std::unique_lock<std::mutex> g(s->mu);
+    if (s->st == St::Aborted) return;
+    words_to_digest(words, s->digest.b);
+    s->matched = (!s->has_expect || s->digest == s->expect) ? 1 : 0;
+    std::vector<Extent> ext;
+    ext.swap(s->extents);
+    s->capacity = 0;
+    const uint64_t size = s->received;
+    const Digest d = s->digest;
+    const int matched = s->matched;
+    g.unlock();
+    std::shared_ptr<Blob> b;
+    if (matched) b = publish(e, d, size, ext);
+    else { free_extents(e, ext); e->st_mismatch++; }
+    g.lock();
+    s->blob = b;
+    s->st = St::Done;
+    g.unlock();
+    s->cv.notify_all();
+}
+
+void reap_cycle(dm_engine *e, Cycle &c)
+{
+    float ms = 0.f;
+    if (c.njobs) {
+        cudaEventElapsedTime(&ms, c.k_start, c.k_end);
+        std::lock_guard<std::mutex> g(e->stat_mu);
+        e->st_kernel_ms += ms;
+    }
+    if (!c.slabs_released) { for (Slab *s : c.slabs) slab_put(e, s); c.slabs.clear(); c.slabs_released = true; }
+    e->st_hashed += c.bytes;
+    for (size_t i = 0; i < c.streams.size(); ++i) {
+        std::shared_ptr<Stream> &sp = c.streams[i];
+        bool free_now = false;
+        {
+            std::lock_guard<std::mutex> g(sp->mu);
+            sp->jobs_inflight--;
+            free_now = sp->st == St::Aborted && sp->jobs_inflight == 0;
+        }
+        if (free_now) {
+            free_extents(e, sp->extents);
+            std::lock_guard<std::mutex> g(e->mu);
+            e->free_slots.push_back(sp->slot);
+        } else if (c.is_final[i]) {
+            complete_stream(e, sp, e->h_digests + 8ull * sp->slot);
+        }
+    }
+    c.streams.clear(); c.is_final.clear();
+    c.njobs = 0; c.bytes = 0; c.busy = false;
+}
+
+// Returns true if anything was launched or recorded.
+bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &work, std::vector<Slab *> &slabs)
+{
+    c.slabs.swap(slabs);
+    c.slabs_released = false;
+    c.njobs = 0; c.bytes = 0;
+    const uint64_t quantum = (uint64_t)e->cfg.slab_bytes * 4;   // bounds one launch's longest lane
+    std::vector<std::shared_ptr<Stream>> again;
+    for (auto &sp : work) {
+        Stream *s = sp.get();
+        std::lock_guard<std::mutex> g(s->mu);
+        {
+            std::lock_guard<std::mutex> gw(e->work_mu);
+            s->dirty = false;
+        }
+        if (s->st == St::Aborted || s->st == St::Done || s->final_issued) continue;
+        if (c.njobs >= e->max_jobs) { again.push_back(sp); continue; }
+        const bool finishing = s->st == St::Finishing;
+        uint64_t n = finishing ? (s->received - s->hash_issued) : ((s->dma_issued - s->hash_issued) & ~63ull);
+        if (!finishing && n == 0) continue;
+        uint64_t contig = 0;
+        uint8_t *src = n ? seg_at(e, s->extents, s->hash_issued, &contig) : nullptr;
+        bool final = finishing;
+        if (n > contig && n) { n = contig; final = false; }          // stop at the extent boundary
+        if (n > quantum) { n = quantum; final = false; }
+        dm::HashJob &jb = c.h_jobs[c.njobs++];
+        jb.src = src; jb.dst = nullptr; jb.nbytes = n; jb.total_len = s->received; jb.slot = s->slot;
+        jb.flags = (s->hash_issued == 0 ? dm::JOB_INIT : 0u) | (final ? dm::JOB_FINAL : 0u);
+        jb.pad_ = 0;
+        s->hash_issued += n;
+        s->jobs_inflight++;
+        if (final) s->final_issued = true;
+        c.bytes += n;
+        c.streams.push_back(sp);
+        c.is_final.push_back(final ? 1 : 0);
+        if (!final && (finishing || ((s->dma_issued - s->hash_issued) & ~63ull))) again.push_back(sp);
+    }
+    work.clear();
+    if (!again.empty()) {
+        std::lock_guard<std::mutex> gw(e->work_mu);
+        for (auto &sp : again)
+            if (!sp->dirty) { sp->dirty = true; e->dirty.push_back(sp); }
+    }
+    if (c.njobs == 0 && c.slabs.empty()) return false;
+
+    // Everything whose DMA was enqueued before this point is covered by these events.
+    for (int i = 0; i < kCopyStreams; ++i) {
+        cudaEventRecord(c.copy_ev[i], e->copy_stream[i]);
+        cudaStreamWaitEvent(e->hash_stream, c.copy_ev[i], 0);
+    }
+    if (c.njobs) {
+        c.deep = c.njobs < dm::kDeepWideCrossover;
+        if (!c.deep) {
+            // lanes of a warp run in lock step: keep neighbours the same length
+            std::vector<uint32_t> order(c.njobs);
+            for (uint32_t i = 0; i < c.njobs; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(),
+                             [&](uint32_t a, uint32_t b) { return c.h_jobs[a].nbytes > c.h_jobs[b].nbytes; });
+            std::vector<dm::HashJob> tmp(c.h_jobs, c.h_jobs + c.njobs);
+            std::vector<std::shared_ptr<Stream>> st2(c.njobs);
+            std::vector<uint8_t> fin2(c.njobs);
+            for (uint32_t i = 0; i < c.njobs; ++i) { c.h_jobs[i] = tmp[order[i]]; st2[i] = c.streams[order[i]]; fin2[i] = c.is_final[order[i]]; }
+            c.streams.swap(st2); c.is_final.swap(fin2);
+        }
+        cudaMemcpyAsync(c.d_jobs, c.h_jobs, sizeof(dm::HashJob) * c.njobs, cudaMemcpyHostToDevice, e->hash_stream);
+        cudaEventRecord(c.k_start, e->hash_stream);
+        if (c.deep) { dm::launch_sha256_deep(c.d_jobs, c.njobs, e->d_states, e->d_digests, e->hash_stream); e->st_deep++; }
+        else { dm::launch_sha256_wide(c.d_jobs, c.njobs, e->d_states, e->d_digests, e->hash_stream); e->st_wide++; }
+        e->st_launches++;
+    }
+    cudaEventRecord(c.k_end, e->hash_stream);
+    c.busy = true;
+    return true;
+}
+
+void pump_main(dm_engine *e)
+{
+    cudaSetDevice(e->device);
+    int head = 0, tail = 0, inflight = 0;   // cycles[tail..head) busy
+    std::vector<std::shared_ptr<Stream>> work;
+    std::vector<Slab *> slabs;
+    for (;;) {
+        // reap in order
+        while (inflight) {
+            Cycle &c = e->cycles[tail];
+            if (!c.slabs_released) {
+                bool done = true;
+                for (int i = 0; i < kCopyStreams; ++i) done = done && cudaEventQuery(c.copy_ev[i]) == cudaSuccess;
+                if (done) { for (Slab *s : c.slabs) slab_put(e, s); c.slabs.clear(); c.slabs_released = true; }
+            }
+            if (cudaEventQuery(c.k_end) != cudaSuccess) break;
+            reap_cycle(e, c);
+            tail = (tail + 1) % kCycles; --inflight;
+        }
+        bool stopping;
+        {
+            std::unique_lock<std::mutex> g(e->work_mu);
+            if (e->dirty.empty() && e->pending_slabs.empty() && !e->stop) {
+                if (inflight) e->work_cv.wait_for(g, std::chrono::microseconds(50));
+                else e->work_cv.wait(g, [&] { return !e->dirty.empty() || !e->pending_slabs.empty() || e->stop; });
+            }
+            stopping = e->stop;
+            if (inflight < kCycles) { work.swap(e->dirty); slabs.swap(e->pending_slabs); }
+        }
+        if (!work.empty() || !slabs.empty()) {
+            if (run_cycle(e, e->cycles[head], work, slabs)) { head = (head + 1) % kCycles; ++inflight; }
+        } else if (inflight == kCycles) {
+            cudaEventSynchronize(e->cycles[tail].k_end);
+        }
+        if (stopping && inflight == 0) {
+            std::lock_guard<std::mutex> g(e->work_mu);
+            if (e->dirty.empty() && e->pending_slabs.empty()) break;
+        }
+    }
+}
+
+// ---- disk tier -----------------------------------------------------------------
+
+Bounce *bounce_get(dm_engine *e)
+{
+    std::unique_lock<std::mutex> g(e->bounce_mu);
+    e->bounce_cv.wait(g, [&] { return !e->bounce_free.empty(); });
+    Bounce *b = e->bounce_free.back();
+    e->bounce_free.pop_back();
+    return b;
+}
+void bounce_put(dm_engine *e, Bounce *b)
+{
+    { std::lock_guard<std::mutex> g(e->bounce_mu); e->bounce_free.push_back(b); }
+    e->bounce_cv.notify_one();
+}
+
+void mkdirs(const std::string &path)
+{
+    for (size_t i = 1; i < path.size(); ++i)
+        if (path[i] == '/') { std::string p = path.substr(0, i); mkdir(p.c_str(), 0755); }
+}
+
+bool spill_one(dm_engine *e, Blob *b)
+{
+    const std::string path = blob_path(e, b->digest.b), tmp = path + ".part";
+    mkdirs(path);
+    int fd = open(tmp.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+    if (fd < 0) return false;
+    Bounce *bn = bounce_get(e);
+    bool ok = true;
+    uint64_t off = 0;
+    while (ok && off < b->size) {
+        const uint64_t n = std::min<uint64_t>(kBounceBytes, b->size - off);
+        uint8_t *dst = bn->host;
+        cudaError_t err = cudaSuccess;
+        for_segments(e, b->extents, off, n, [&](uint8_t *dev, uint64_t len) {
+            if (err == cudaSuccess) err = cudaMemcpyAsync(dst, dev, len, cudaMemcpyDeviceToHost, bn->stream);
+            dst += len;
+        });
+        if (err == cudaSuccess) err = cudaStreamSynchronize(bn->stream);
+        if (err != cudaSuccess) { ok = false; break; }
+        e->st_d2h += n;
+        uint64_t w = 0;
+        while (w < n) {
+            ssize_t r = write(fd, bn->host + w, n - w);
+            if (r < 0) { if (errno == EINTR) continue; ok = false; break; }
+            w += (uint64_t)r;
+        }
+        off += n;
+    }
+    bounce_put(e, bn);
+    close(fd);
+    if (ok) ok = rename(tmp.c_str(), path.c_str()) == 0;
+    if (ok) write_sidecar(path + ".meta", *b);
+    else unlink(tmp.c_str());
+    return ok;
+}
+
+void spill_main(dm_engine *e)
+{
+    cudaSetDevice(e->device);
+    for (;;) {
+        std::shared_ptr<Blob> b;
+        {
+            std::unique_lock<std::mutex> g(e->spill_mu);
+            e->spill_cv.wait(g, [&] { return !e->spill_q.empty() || e->stop; });
+            if (e->spill_q.empty()) break;
+            b = e->spill_q.front();
+            e->spill_q.pop_front();
+        }
+        bool have;
+        {
+            std::lock_guard<std::mutex> g(e->mu);
+            have = b->in_hbm;
+            if (have) b->readers++;        // pin against eviction while copying out
+        }
+        bool ok = have && spill_one(e, b.get());
+        {
+            std::lock_guard<std::mutex> g(e->mu);
+            if (have) b->readers--;
+            b->on_disk = ok;
+            b->spill_done = true;
+        }
+        {
+            std::lock_guard<std::mutex> g(e->spill_mu);
+        }
+        e->spill_done_cv.notify_all();
+    }
+}
+
+std::shared_ptr<Stream> find_stream(dm_engine *e, uint64_t id)
+{
+    std::lock_guard<std::mutex> g(e->mu);
+    auto it = e->streams.find(id);
+    return it == e->streams.end() ? nullptr : it->second;
+}
+
+void drop_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, bool release_slot)
+{
+    std::lock_guard<std::mutex> g(e->mu);
+    e->streams.erase(sp->id);
+    if (release_slot) e->free_slots.push_back(sp->slot);
+}
+
+int ensure_ingest_scratch(dm_engine *e, uint32_t n)
+{
+    if (n <= e->ing_cap) return DM_OK;
+    const uint32_t cap = std::max<uint32_t>(n, 4096);
+    if (e->ing_states) { cudaFree(e->ing_states); cudaFree(e->ing_digests); cudaFree(e->ing_jobs_d);
+                         cudaFreeHost(e->ing_jobs_h); cudaFreeHost(e->ing_digests_h); e->ing_cap = 0; }
+    CU_TRY(cudaMalloc(&e->ing_states, 32ull * cap));
+    CU_TRY(cudaMalloc(&e->ing_digests, 32ull * cap));
+    CU_TRY(cudaMalloc(&e->ing_jobs_d, sizeof(dm::HashJob) * (uint64_t)cap));
+    CU_TRY(cudaHostAlloc(&e->ing_jobs_h, sizeof(dm::HashJob) * (uint64_t)cap, cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&e->ing_digests_h, 32ull * cap, cudaHostAllocDefault));
+    e->ing_cap = cap;
+    return DM_OK;
+}
+
+}  // namespace
+
+// ============================================================================
+// C ABI
+// ============================================================================
+extern "C" {
+
+uint32_t dm_abi_version(void) { return DM_ABI_VERSION; }
+
+const char *dm_last_error(void) { return g_last_error.c_str(); }
+
+const char *dm_strerror(int err)
+{
+    switch (err) {
+    case DM_OK: return "ok";
+    case DM_EINVAL: return "invalid argument";
+    case DM_ENOMEM: return "out of HBM arena, pinned ring or stream slots";
+    case DM_ENOENT: return "digest not in the content-addressed store";
+    case DM_ECUDA: return "CUDA runtime error";
+    case DM_ESTATE: return "call not valid in this stream state";
+    case DM_EIO: return "disk tier I/O error";
+    case DM_ENODEV: return "no usable CUDA device";
+    case DM_ERANGE: return "offset beyond blob end";
+    default: return "unknown error";
+    }
+}
+
+int dm_device_count(void)
+{
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess) { fail_cuda(err, "cudaGetDeviceCount"); return DM_ENODEV; }
+    return n;
+}
+
+uint32_t dm_shard_of(const uint8_t digest[32], uint32_t n_shards)
+{
+    if (!digest || n_shards <= 1) return 0;
+    const uint32_t prefix = ((uint32_t)digest[0] << 8) | digest[1];
+    return (uint32_t)(((uint64_t)prefix * n_shards) >> 16);
+}
+
+void dm_engine_destroy(dm_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    {
+        std::lock_guard<std::mutex> g(e->work_mu);
+        e->stop = true;
+    }
+    e->work_cv.notify_all();
+    e->slab_cv.notify_all();
+    if (e->pump.joinable()) e->pump.join();
+    {
+        std::lock_guard<std::mutex> g(e->spill_mu);
+    }
+    e->spill_cv.notify_all();
+    if (e->spiller.joinable()) e->spiller.join();
+    cudaDeviceSynchronize();
+    for (auto &kv : e->readers) if (kv.second->fd >= 0) close(kv.second->fd);
+    for (Cycle &c : e->cycles) {
+        for (int i = 0; i < kCopyStreams; ++i) if (c.copy_ev[i]) cudaEventDestroy(c.copy_ev[i]);
+        if (c.k_start) cudaEventDestroy(c.k_start);
+        if (c.k_end) cudaEventDestroy(c.k_end);
+        if (c.h_jobs) cudaFreeHost(c.h_jobs);
+        if (c.d_jobs) cudaFree(c.d_jobs);
+    }
+    for (Bounce &b : e->bounce_store) { if (b.host) cudaFreeHost(b.host); if (b.stream) cudaStreamDestroy(b.stream); }
+    if (e->ing_states) { cudaFree(e->ing_states); cudaFree(e->ing_digests); cudaFree(e->ing_jobs_d);
+                         cudaFreeHost(e->ing_jobs_h); cudaFreeHost(e->ing_digests_h); }
+    if (e->ing_ev0) cudaEventDestroy(e->ing_ev0);
+    if (e->ing_ev1) cudaEventDestroy(e->ing_ev1);
+    if (e->d_states) cudaFree(e->d_states);
+    if (e->h_digests) cudaFreeHost(e->h_digests);
+    if (e->ring) cudaFreeHost(e->ring);
+    if (e->arena_base) cudaFree(e->arena_base);
+    for (int i = 0; i < kCopyStreams; ++i) if (e->copy_stream[i]) cudaStreamDestroy(e->copy_stream[i]);
+    if (e->hash_stream) cudaStreamDestroy(e->hash_stream);
+    if (e->ingest_stream) cudaStreamDestroy(e->ingest_stream);
+    if (e->util_stream) cudaStreamDestroy(e->util_stream);
+    delete e;
+}
+
+int dm_engine_create(const dm_config *cfg, dm_engine **out)
+{
+    if (!cfg || !out || cfg->struct_size != sizeof(dm_config)) return fail(DM_EINVAL, "dm_config missing or wrong struct_size");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev == 0) {
+        fail_cuda(err, "cudaGetDeviceCount");
+        return DM_ENODEV;   // no CPU fallback on the hash path
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(DM_ENODEV, "device ordinal out of range");
+    if (cfg->slab_bytes && (cfg->slab_bytes % 256)) return fail(DM_EINVAL, "slab_bytes must be a multiple of 256");
+    if (cfg->flags & DM_F_NO_HBM_CAS) return fail(DM_EINVAL, "DM_F_NO_HBM_CAS: use dm_ingest_device(DM_ING_HASH_ONLY)");
+
+    dm_engine *e = new dm_engine();
+    e->cfg = *cfg;
+    e->device = cfg->device;
+    if (cfg->cas_dir) e->cas_dir = cfg->cas_dir;
+    e->cfg.cas_dir = nullptr;
+    if (!e->cfg.slab_bytes) e->cfg.slab_bytes = 1u << 20;
+    if (!e->cfg.ring_bytes) e->cfg.ring_bytes = 256ull << 20;
+    if (!e->cfg.max_streams) e->cfg.max_streams = 65536;
+    if (e->cfg.ring_bytes < 4ull * e->cfg.slab_bytes) e->cfg.ring_bytes = 4ull * e->cfg.slab_bytes;
+
+#define CU_INIT(expr)                                                                   \
+    do {                                                                                \
+        cudaError_t cu_err_ = (expr);                                                   \
+        if (cu_err_ != cudaSuccess) { fail_cuda(cu_err_, #expr); dm_engine_destroy(e); return DM_ECUDA; } \
+    } while (0)
+
+    CU_INIT(cudaSetDevice(e->device));
+    cudaDeviceProp prop;
+    CU_INIT(cudaGetDeviceProperties(&prop, e->device));
+    e->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) { fail(DM_ENODEV, "kernels are built for sm_100a only"); dm_engine_destroy(e); return DM_ENODEV; }
+
+    for (int i = 0; i < kCopyStreams; ++i) CU_INIT(cudaStreamCreateWithFlags(&e->copy_stream[i], cudaStreamNonBlocking));
+    CU_INIT(cudaStreamCreateWithFlags(&e->hash_stream, cudaStreamNonBlocking));
+    CU_INIT(cudaStreamCreateWithFlags(&e->ingest_stream, cudaStreamNonBlocking));
+    CU_INIT(cudaStreamCreateWithFlags(&e->util_stream, cudaStreamNonBlocking));
+    CU_INIT(cudaEventCreate(&e->ing_ev0));
+    CU_INIT(cudaEventCreate(&e->ing_ev1));
+
+    if (!e->cfg.hbm_cas_bytes) {
+        size_t fr = 0, tot = 0;
+        CU_INIT(cudaMemGetInfo(&fr, &tot));
+        e->cfg.hbm_cas_bytes = fr / 2;
+    }
+    e->cfg.hbm_cas_bytes = round_up(e->cfg.hbm_cas_bytes, kAlign);
+    CU_INIT(cudaMalloc(&e->arena_base, e->cfg.hbm_cas_bytes));
+    e->arena.reset(e->cfg.hbm_cas_bytes);
+
+    const uint64_t nslab = e->cfg.ring_bytes / e->cfg.slab_bytes;
+    CU_INIT(cudaHostAlloc(&e->ring, nslab * e->cfg.slab_bytes, cudaHostAllocDefault));
+    e->slab_store.resize(nslab);
+    for (uint64_t i = 0; i < nslab; ++i) { e->slab_store[i].host = e->ring + i * e->cfg.slab_bytes; e->slab_free.push_back(&e->slab_store[i]); }
+
+    CU_INIT(cudaMalloc(&e->d_states, 32ull * e->cfg.max_streams));
+    CU_INIT(cudaHostAlloc(&e->h_digests, 32ull * e->cfg.max_streams, cudaHostAllocMapped));
+    CU_INIT(cudaHostGetDevicePointer((void **)&e->d_digests, e->h_digests, 0));
+    e->free_slots.reserve(e->cfg.max_streams);
+    for (uint32_t i = e->cfg.max_streams; i-- > 0;) e->free_slots.push_back(i);
+
+    e->max_jobs = e->cfg.max_streams;
+    for (Cycle &c : e->cycles) {
+        for (int i = 0; i < kCopyStreams; ++i) CU_INIT(cudaEventCreateWithFlags(&c.copy_ev[i], cudaEventDisableTiming));
+        CU_INIT(cudaEventCreate(&c.k_start));
+        CU_INIT(cudaEventCreate(&c.k_end));
+        CU_INIT(cudaHostAlloc(&c.h_jobs, sizeof(dm::HashJob) * (uint64_t)e->max_jobs, cudaHostAllocDefault));
+        CU_INIT(cudaMalloc(&c.d_jobs, sizeof(dm::HashJob) * (uint64_t)e->max_jobs));
+    }
+    e->bounce_store.resize(kBounces);
+    for (Bounce &b : e->bounce_store) {
+        CU_INIT(cudaHostAlloc(&b.host, kBounceBytes, cudaHostAllocDefault));
+        CU_INIT(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+        e->bounce_free.push_back(&b);
+    }
+#undef CU_INIT
+    if (!e->cas_dir.empty()) mkdirs(e->cas_dir + "/blobs/sha256/x");
+    e->pump = std::thread(pump_main, e);
+    if (!e->cas_dir.empty()) e->spiller = std::thread(spill_main, e);
+    *out = e;
+    return DM_OK;
+}
+
+int dm_engine_stats(dm_engine *e, dm_stats *o)
+{
+    if (!e || !o) return fail(DM_EINVAL, "null argument");
+    memset(o, 0, sizeof *o);
+    o->bytes_ingested = e->st_ingested; o->bytes_hashed = e->st_hashed; o->bytes_served = e->st_served;
+    o->blobs_committed = e->st_committed; o->blobs_mismatched = e->st_mismatch;
+    o->kernel_launches = e->st_launches; o->launches_wide = e->st_wide; o->launches_deep = e->st_deep;
+    { std::lock_guard<std::mutex> g(e->stat_mu); o->kernel_ms = e->st_kernel_ms; }
+    o->h2d_bytes = e->st_h2d; o->d2h_bytes = e->st_d2h;
+    { std::lock_guard<std::mutex> g(e->arena_mu); o->hbm_cas_used = e->arena.used(); o->hbm_cas_capacity = e->arena.capacity(); }
+    { std::lock_guard<std::mutex> g(e->mu); o->open_streams = e->streams.size(); }
+    return DM_OK;
+}
+
+// ---- ingest ------------------------------------------------------------------
+
+int dm_stream_open(dm_engine *e, const uint8_t expect[32], uint64_t size_hint, uint64_t *id)
+{
+    if (!e || !id) return fail(DM_EINVAL, "null argument");
+    auto sp = std::make_shared<Stream>();
+    if (expect) { sp->has_expect = true; memcpy(sp->expect.b, expect, 32); }
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        if (e->free_slots.empty()) return fail(DM_ENOMEM, "max_streams reached");
+        sp->slot = e->free_slots.back();
+        e->free_slots.pop_back();
+        sp->id = e->next_id++;
+    }
+    if (size_hint) {
+        cudaSetDevice(e->device);
+        std::lock_guard<std::mutex> g(sp->mu);
+        Extent x;
+        if (!arena_alloc(e, size_hint, &x)) {
+            std::lock_guard<std::mutex> g2(e->mu);
+            e->free_slots.push_back(sp->slot);
+            return fail(DM_ENOMEM, "HBM CAS arena exhausted");
+        }
+        sp->extents.push_back(x);
+        sp->capacity = x.len;
+    }
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        e->streams[sp->id] = sp;
+    }
+    *id = sp->id;
+    return DM_OK;
+}
+
+int dm_stream_write(dm_engine *e, uint64_t id, const void *buf, size_t len)
+{
+    if (!e || (!buf && len)) return fail(DM_EINVAL, "null argument");
+    auto sp = find_stream(e, id);
+    if (!sp) return fail(DM_EINVAL, "unknown stream id");
+    cudaSetDevice(e->device);
+    Stream *s = sp.get();
+    std::unique_lock<std::mutex> g(s->mu);
+    if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open for write");
+    const uint8_t *p = static_cast<const uint8_t *>(buf);
+    const uint32_t slab_bytes = e->cfg.slab_bytes;
+    while (len) {
+        if (!s->cur) {
+            int rc = take_slab(e, s, g);
+            if (rc != DM_OK) return rc;
+        }
+        const size_t n = std::min<size_t>(len, slab_bytes - s->cur_fill);
+        memcpy(s->cur->host + s->cur_fill, p, n);
+        s->cur_fill += (uint32_t)n; s->received += n; p += n; len -= n;
+        e->st_ingested += n;
+        if (s->cur_fill == slab_bytes) {
+            int rc = submit_slab(e, sp);
+            if (rc != DM_OK) return rc;
+        }
+    }
+    return DM_OK;
+}
+
+int dm_stream_acquire(dm_engine *e, uint64_t id, void **ptr, size_t *cap)
+{
+    if (!e || !ptr || !cap) return fail(DM_EINVAL, "null argument");
+    auto sp = find_stream(e, id);
+    if (!sp) return fail(DM_EINVAL, "unknown stream id");
+    Stream *s = sp.get();
+    std::unique_lock<std::mutex> g(s->mu);
+    if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open or window outstanding");
+    if (!s->cur) {
+        int rc = take_slab(e, s, g);
+        if (rc != DM_OK) return rc;
+    }
+    *ptr = s->cur->host + s->cur_fill;
+    *cap = e->cfg.slab_bytes - s->cur_fill;
+    s->window_out = true;
+    return DM_OK;
+}
+
+int dm_stream_commit(dm_engine *e, uint64_t id, size_t len)
+{
+    if (!e) return fail(DM_EINVAL, "null argument");
+    auto sp = find_stream(e, id);
+    if (!sp) return fail(DM_EINVAL, "unknown stream id");
+    cudaSetDevice(e->device);
+    Stream *s = sp.get();
+    std::lock_guard<std::mutex> g(s->mu);
+    if (!s->window_out) return fail(DM_ESTATE, "no window outstanding");
+    if (len > e->cfg.slab_bytes - s->cur_fill) return fail(DM_EINVAL, "commit larger than the window");
+    s->window_out = false;
+    s->cur_fill += (uint32_t)len; s->received += len;
+    e->st_ingested += len;
+    if (s->cur_fill == e->cfg.slab_bytes) return submit_slab(e, sp);
+    return DM_OK;
+}
+
+int dm_stream_finish(dm_engine *e, uint64_t id, uint8_t digest_out[32], int *matched)
+{
+    if (!e) return fail(DM_EINVAL, "null argument");
+    auto sp = find_stream(e, id);
+    if (!sp) return fail(DM_EINVAL, "unknown stream id");
+    cudaSetDevice(e->device);
+    Stream *s = sp.get();
+    std::shared_ptr<Blob> blob;
+    {
+        std::unique_lock<std::mutex> g(s->mu);
+        if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open");
+        int rc = submit_slab(e, sp);
+        if (rc != DM_OK) return rc;
+        s->st = St::Finishing;
+        mark_dirty(e, sp, nullptr);
+        s->cv.wait(g, [&] { return s->st == St::Done; });
+        if (digest_out) memcpy(digest_out, s->digest.b, 32);
+        if (matched) *matched = s->matched;
+        blob = s->blob;
+    }
+    drop_stream(e, sp, true);
+    if (blob && (e->cfg.flags & DM_F_DISK_SYNC) && !e->cas_dir.empty()) {
+        std::unique_lock<std::mutex> g(e->spill_mu);
+        e->spill_done_cv.wait(g, [&] { std::lock_guard<std::mutex> g2(e->mu); return blob->spill_done; });
+        std::lock_guard<std::mutex> g2(e->mu);
+        if (!blob->on_disk) return fail(DM_EIO, "disk tier write failed");
+    }
+    return DM_OK;
+}
+
+int dm_stream_abort(dm_engine *e, uint64_t id)
+{
+    if (!e) return fail(DM_EINVAL, "null argument");
+    auto sp = find_stream(e, id);
+    if (!sp) return fail(DM_EINVAL, "unknown stream id");
+    Stream *s = sp.get();
+    bool free_now;
+    {
+        std::lock_guard<std::mutex> g(s->mu);
+        if (s->st == St::Done || s->st == St::Aborted) return fail(DM_ESTATE, "stream already closed");
+        if (s->cur) { slab_put(e, s->cur); s->cur = nullptr; s->cur_fill = 0; }
+        s->st = St::Aborted;
+        free_now = s->jobs_inflight == 0;
+    }
+    if (free_now) free_extents(e, s->extents);
+    drop_stream(e, sp, free_now);   // otherwise the pump releases slot + extents at reap
+    s->cv.notify_all();
+    return DM_OK;
+}
+
+// ---- hit serving ---------------------------------------------------------------
+
+int dm_cache_contains(dm_engine *e, const uint8_t digest[32], uint64_t *size)
+{
+    if (!e || !digest) return fail(DM_EINVAL, "null argument");
+    Digest d;
+    memcpy(d.b, digest, 32);
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        auto it = e->blobs.find(d);
+        if (it != e->blobs.end() && (it->second->in_hbm || it->second->on_disk)) {
+            if (size) *size = it->second->size;
+            return DM_OK;
+        }
+    }
+    if (!e->cas_dir.empty()) {
+        struct stat st;
+        if (stat(blob_path(e, digest).c_str(), &st) == 0) { if (size) *size = (uint64_t)st.st_size; return DM_OK; }
+    }
+    return DM_ENOENT;
+}
+
+int dm_cache_open(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size)
+{
+    if (!e || !digest || !reader) return fail(DM_EINVAL, "null argument");
+    Digest d;
+    memcpy(d.b, digest, 32);
+    auto r = std::make_shared<Reader>();
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        auto it = e->blobs.find(d);
+        if (it != e->blobs.end() && it->second->in_hbm) {
+            r->blob = it->second;
+            r->blob->readers++;
+            r->blob->tick = ++e->tick;
+            r->size = r->blob->size;
+        }
+    }
+    if (!r->blob) {
+        if (e->cas_dir.empty()) return DM_ENOENT;
+        r->fd = open(blob_path(e, digest).c_str(), O_RDONLY);
+        if (r->fd < 0) return DM_ENOENT;
+        struct stat st;
+        fstat(r->fd, &st);
+        r->size = (uint64_t)st.st_size;
+    }
+    std::lock_guard<std::mutex> g(e->mu);
+    const uint64_t id = e->next_id++;
+    e->readers[id] = r;
+    *reader = id;
+    if (size) *size = r->size;
+    return DM_OK;
+}
+
+int dm_cache_read(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t len, size_t *nread)
+{
+    if (!e || (!buf && len)) return fail(DM_EINVAL, "null argument");
+    std::shared_ptr<Reader> r;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        auto it = e->readers.find(reader);
+        if (it == e->readers.end()) return fail(DM_EINVAL, "unknown reader id");
+        r = it->second;
+    }
+    if (nread) *nread = 0;
+    if (off > r->size) return fail(DM_ERANGE, "offset beyond blob end");
+    len = (size_t)std::min<uint64_t>(len, r->size - off);
+    if (len == 0) return DM_OK;
+    uint8_t *out = static_cast<uint8_t *>(buf);
+    if (!r->blob) {
+        size_t got = 0;
+        while (got < len) {
+            ssize_t n = pread(r->fd, out + got, len - got, (off_t)(off + got));
+            if (n < 0) { if (errno == EINTR) continue; return fail(DM_EIO, "pread failed"); }
+            if (n == 0) break;
+            got += (size_t)n;
+        }
+        if (nread) *nread = got;
+        e->st_served += got;
+        return DM_OK;
+    }
+    cudaSetDevice(e->device);
+    Bounce *bn = bounce_get(e);
+    size_t done = 0;
+    int rc = DM_OK;
+    while (done < len) {
+        const size_t n = std::min(len - done, kBounceBytes);
+        uint8_t *dst = bn->host;
+        cudaError_t err = cudaSuccess;
+        for_segments(e, r->blob->extents, off + done, n, [&](uint8_t *dev, uint64_t l) {
+            if (err == cudaSuccess) err = cudaMemcpyAsync(dst, dev, l, cudaMemcpyDeviceToHost, bn->stream);
+            dst += l;
+        });
+        if (err == cudaSuccess) err = cudaStreamSynchronize(bn->stream);
+        if (err != cudaSuccess) { rc = fail_cuda(err, "cudaMemcpyAsync(D2H)"); break; }
+        memcpy(out + done, bn->host, n);
+        done += n;
+    }
+    bounce_put(e, bn);
+    e->st_d2h += done; e->st_served += done;
+    if (nread) *nread = done;
+    return rc;
+}
+
+int dm_cache_close(dm_engine *e, uint64_t reader)
+{
+    if (!e) return fail(DM_EINVAL, "null argument");
+    std::shared_ptr<Reader> r;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        auto it = e->readers.find(reader);
+        if (it == e->readers.end()) return fail(DM_EINVAL, "unknown reader id");
+        r = it->second;
+        e->readers.erase(it);
+        if (r->blob) r->blob->readers--;
+    }
+    if (r->fd >= 0) close(r->fd);
+    return DM_OK;
+}
+
+int dm_cache_evict(dm_engine *e, const uint8_t digest[32])
+{
+    if (!e || !digest) return fail(DM_EINVAL, "null argument");
+    Digest d;
+    memcpy(d.b, digest, 32);
+    std::shared_ptr<Blob> b;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        auto it = e->blobs.find(d);
+        if (it == e->blobs.end() || !it->second->in_hbm) return DM_ENOENT;
+        if (it->second->readers) return fail(DM_ESTATE, "blob has open readers");
+        b = it->second;
+        b->in_hbm = false;
+        if (!b->on_disk) e->blobs.erase(it);
+    }
+    free_extents(e, b->extents);
+    return DM_OK;
+}
+
+int dm_cache_device_extents(dm_engine *e, uint64_t reader, void **dev_ptrs, uint64_t *lens, uint32_t max_ext)
+{
+    if (!e) return fail(DM_EINVAL, "null argument");
+    std::lock_guard<std::mutex> g(e->mu);
+    auto it = e->readers.find(reader);
+    if (it == e->readers.end()) return fail(DM_EINVAL, "unknown reader id");
+    if (!it->second->blob) return fail(DM_ESTATE, "blob is on the disk tier only");
+    const auto &ext = it->second->blob->extents;
+    uint64_t left = it->second->blob->size;
+    for (uint32_t i = 0; i < ext.size() && i < max_ext; ++i) {
+        if (dev_ptrs) dev_ptrs[i] = e->arena_base + ext[i].off;
+        if (lens) lens[i] = std::min(left, ext[i].len);
+        left -= std::min(left, ext[i].len);
+    }
+    return (int)ext.size();
+}
+
+// ---- device-resident ingest -------------------------------------------------------
+
+int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets, const uint64_t *lengths,
+                     uint32_t n, const uint8_t *expect, uint8_t *digests_out, uint8_t *matched_out,
+                     uint32_t flags, double *kernel_ms)
+{
+    if (!e || ((!offsets || !lengths || !dev_base) && n)) return fail(DM_EINVAL, "null argument");
+    if (kernel_ms) *kernel_ms = 0.0;
+    if (n == 0) return DM_OK;
+    if (((uintptr_t)dev_base) & 15) return fail(DM_EINVAL, "dev_base must be 16-byte aligned");
+    for (uint32_t i = 0; i < n; ++i)
+        if (offsets[i] & 15) return fail(DM_EINVAL, "offsets must be multiples of 16");
+    cudaSetDevice(e->device);
+    std::lock_guard<std::mutex> gi(e->ingest_mu);
+    int rc = ensure_ingest_scratch(e, n);
+    if (rc != DM_OK) return rc;
+    const bool hash_only = (flags & DM_ING_HASH_ONLY) != 0;
+    std::vector<std::vector<Extent>> ext(n);
+    auto cleanup = [&] { for (auto &v : ext) if (!v.empty()) free_extents(e, v); };
+    if ((flags & DM_ING_REPLACE) && expect && !hash_only)
+        for (uint32_t i = 0; i < n; ++i) dm_cache_evict(e, expect + 32ull * i);
+    const uint8_t *base = static_cast<const uint8_t *>(dev_base);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t len = lengths[i];
+        dm::HashJob &jb = e->ing_jobs_h[i];
+        jb.src = base + offsets[i]; jb.dst = nullptr; jb.nbytes = len; jb.total_len = len;
+        jb.slot = i; jb.flags = dm::JOB_INIT | dm::JOB_FINAL; jb.pad_ = 0;
+        if (!hash_only) {
+            Extent x;
+            if (!arena_alloc(e, len, &x)) { cleanup(); return fail(DM_ENOMEM, "HBM CAS arena exhausted"); }
+            ext[i].push_back(x);
+            jb.dst = e->arena_base + x.off;
+        }
+        total += len;
+    }
+    bool deep = n < dm::kDeepWideCrossover;
+    if (flags & DM_ING_FORCE_WIDE) deep = false;
+    if (flags & DM_ING_FORCE_DEEP) deep = true;
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    if (!deep) {
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            return e->ing_jobs_h[a].nbytes > e->ing_jobs_h[b].nbytes; });
+        std::vector<dm::HashJob> tmp(e->ing_jobs_h, e->ing_jobs_h + n);
+        for (uint32_t i = 0; i < n; ++i) e->ing_jobs_h[i] = tmp[order[i]];   // slot keeps the caller's index
+    }
+    cudaStream_t st = e->ingest_stream;
+    cudaError_t err = cudaMemcpyAsync(e->ing_jobs_d, e->ing_jobs_h, sizeof(dm::HashJob) * (uint64_t)n, cudaMemcpyHostToDevice, st);
+    if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev0, st);
+    if (err == cudaSuccess)
+        err = deep ? dm::launch_sha256_deep(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st)
+                   : dm::launch_sha256_wide(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st);
+    if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev1, st);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(e->ing_digests_h, e->ing_digests, 32ull * n, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) { cleanup(); return fail_cuda(err, "dm_ingest_device launch"); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->ing_ev0, e->ing_ev1);
+    if (kernel_ms) *kernel_ms = ms;
+    { std::lock_guard<std::mutex> g(e->stat_mu); e->st_kernel_ms += ms; }
+    e->st_launches++; (deep ? e->st_deep : e->st_wide)++;
+    e->st_hashed += total;
+    for (uint32_t i = 0; i < n; ++i) {
+        Digest d;
+        words_to_digest(e->ing_digests_h + 8ull * i, d.b);
+        if (digests_out) memcpy(digests_out + 32ull * i, d.b, 32);
+        const int ok = (!expect || memcmp(expect + 32ull * i, d.b, 32) == 0) ? 1 : 0;
+        if (matched_out) matched_out[i] = (uint8_t)ok;
+        if (hash_only) continue;
+        if (ok) publish(e, d, lengths[i], ext[i]);
+        else { free_extents(e, ext[i]); e->st_mismatch++; }
+    }
+    return DM_OK;
+}
+
+// ---- synthetic bytes ---------------------------------------------------------------
+
+void dm_synth_fill_host(uint64_t seed, uint64_t blob, uint64_t byte_off, void *dst, size_t len)
+{
+    const uint64_t key = dm_blob_key(seed, blob);
+    uint8_t *p = static_cast<uint8_t *>(dst);
+    uint64_t j = byte_off;
+    while (len && (j & 7)) { *p++ = (uint8_t)(dm_blob_word_k(key, j >> 3) >> (8 * (j & 7))); ++j; --len; }
+    while (len >= 8) { const uint64_t w = dm_blob_word_k(key, j >> 3); memcpy(p, &w, 8); p += 8; j += 8; len -= 8; }
+    while (len) { *p++ = (uint8_t)(dm_blob_word_k(key, j >> 3) >> (8 * (j & 7))); ++j; --len; }
+}
+
+int dm_synth_fill_device(dm_engine *e, uint64_t seed, uint64_t blob, uint64_t byte_off, void *dev_dst, size_t len)
+{
+    if (!e || (!dev_dst && len)) return fail(DM_EINVAL, "null argument");
+    cudaSetDevice(e->device);
+    CU_TRY(dm::launch_synth_fill(seed, blob, byte_off, dev_dst, len, e->util_stream));
+    CU_TRY(cudaStreamSynchronize(e->util_stream));
+    return DM_OK;
+}
+
+int dm_synth_fill_device_many(dm_engine *e, uint64_t seed, uint64_t first_blob, void *dev_base,
+                              const uint64_t *offsets, const uint64_t *lengths, uint32_t n)
+{
+    if (!e || ((!offsets || !lengths || !dev_base) && n)) return fail(DM_EINVAL, "null argument");
+    if (n == 0) return DM_OK;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (offsets[i] & 15) return fail(DM_EINVAL, "offsets must be multiples of 16");
+        if (i && offsets[i] < offsets[i - 1] + lengths[i - 1]) return fail(DM_EINVAL, "blobs must be ascending and disjoint");
+    }
+    cudaSetDevice(e->device);
+    uint64_t *d_tab = nullptr;
+    CU_TRY(cudaMalloc(&d_tab, 16ull * n));
+    cudaError_t err = cudaMemcpyAsync(d_tab, offsets, 8ull * n, cudaMemcpyHostToDevice, e->util_stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d_tab + n, lengths, 8ull * n, cudaMemcpyHostToDevice, e->util_stream);
+    if (err == cudaSuccess)
+        err = dm::launch_synth_fill_many(seed, first_blob, dev_base, d_tab, d_tab + n, n, offsets[0],
+                                         offsets[n - 1] + lengths[n - 1] - offsets[0], e->util_stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->util_stream);
+    cudaFree(d_tab);
+    if (err != cudaSuccess) return fail_cuda(err, "dm_synth_fill_device_many");
+    return DM_OK;
+}
+
+}  // extern "C"

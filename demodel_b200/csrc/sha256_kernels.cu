@@ -1,0 +1,434 @@
+// Multi-buffer SHA-256 for sm_100a: the hot path of the blob hash-and-cache
+// engine.  Pure 32-bit integer work (SHF / LOP3 / IADD3 / IMAD) — no tensor
+// cores, no floating point.  Two kernels share the round function:
+//
+//   sha256_wide_kernel  one 32-bit lane per live stream (the multi-buffer
+//                       form north_star describes): W[16] and the eight
+//                       state words live in registers, round constants are
+//                       instruction immediates, each lane pulls one whole
+//                       128-byte line (two blocks) per iteration.  Throughput
+//                       bound by the ALU/FMA issue rate; needs >~10^4 streams
+//                       to fill the chip.
+//   sha256_deep_kernel  one warp per stream, for few live streams.  SHA-256's
+//                       serial chain is only the 64 rounds; the message
+//                       schedule is state-independent.  The 32 lanes expand
+//                       the schedules of 32 consecutive blocks in parallel
+//                       (coalesced 2 KiB load) and stage W[t]+K[t] in shared
+//                       memory; then the warp runs the 32x64 dependent rounds
+//                       reading one broadcast LDS.128 per 4 rounds.  ~1.5x the
+//                       per-stream rate of the lane-per-stream form.
+//
+// Both optionally write every byte they read to `dst` (the blob's CAS
+// extent), so hash-and-cache moves 1 B read + 1 B written per blob byte.
+//
+// The digest definition is FIPS 180-4 (what Go crypto/sha256 implements —
+// the reference names it in BASELINE.json north_star but holds no call site:
+// /root/reference/cmd/demodel/start.go:201-204 returns resp unchanged).
+#include "sha256_kernels.cuh"
+#include "blobgen.h"
+
+namespace dm {
+namespace {
+
+// ---------------------------------------------------------------------------
+// FIPS 180-4 §4.1.2 functions as single SASS ops.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rotr(uint32_t x, uint32_t n) { return __funnelshift_r(x, x, n); }
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t f_ch(uint32_t e, uint32_t f, uint32_t g)
+{
+    uint32_t d;   // (e & f) ^ (~e & g)
+    asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(e), "r"(f), "r"(g));
+    return d;
+}
+__device__ __forceinline__ uint32_t f_maj(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;   // (a & b) ^ (a & c) ^ (b & c)
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t big_sigma0(uint32_t x) { return xor3(rotr(x, 2), rotr(x, 13), rotr(x, 22)); }
+__device__ __forceinline__ uint32_t big_sigma1(uint32_t x) { return xor3(rotr(x, 6), rotr(x, 11), rotr(x, 25)); }
+__device__ __forceinline__ uint32_t small_sigma0(uint32_t x) { return xor3(rotr(x, 7), rotr(x, 18), x >> 3); }
+__device__ __forceinline__ uint32_t small_sigma1(uint32_t x) { return xor3(rotr(x, 17), rotr(x, 19), x >> 10); }
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// FIPS 180-4 §4.2.2.  Indexed only with compile-time constants inside fully
+// unrolled loops, so every use folds to an instruction immediate.
+#define DM_K256_TABLE                                                                        \
+    0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, \
+    0xab1c5ed5u, 0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, \
+    0x9bdc06a7u, 0xc19bf174u, 0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, \
+    0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau, 0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, \
+    0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u, 0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, \
+    0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u, 0xa2bfe8a1u, 0xa81a664bu, \
+    0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u, 0x19a4c116u, \
+    0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u, \
+    0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, \
+    0xc67178f2u
+
+// One round, FIPS 180-4 §6.2.2 step 3, with the a..h rotation done by
+// renaming: v[] is indexed modulo 8 by the (compile-time) round number.
+//   T1 = h + S1(e) + Ch(e,f,g) + (K+W);  d += T1;  h = T1 + S0(a) + Maj(a,b,c)
+#define DM_ROUND(v, t, kw)                                                              \
+    do {                                                                                \
+        uint32_t t1_ = v[(7 - (t)) & 7] + big_sigma1(v[(4 - (t)) & 7]) +                \
+                       f_ch(v[(4 - (t)) & 7], v[(5 - (t)) & 7], v[(6 - (t)) & 7]) + (kw); \
+        uint32_t t2_ = big_sigma0(v[(0 - (t)) & 7]) +                                   \
+                       f_maj(v[(0 - (t)) & 7], v[(1 - (t)) & 7], v[(2 - (t)) & 7]);     \
+        v[(3 - (t)) & 7] += t1_;                                                        \
+        v[(7 - (t)) & 7] = t1_ + t2_;                                                   \
+    } while (0)
+
+// Whole-block compression with everything in registers.  w[] holds the 16
+// big-endian message words and is clobbered (rolling 16-word schedule).
+__device__ __forceinline__ void compress_regs(uint32_t (&s)[8], uint32_t (&w)[16])
+{
+    constexpr uint32_t K[64] = {DM_K256_TABLE};
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = s[i];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) DM_ROUND(v, t, K[t] + w[t]);
+#pragma unroll
+    for (int t = 16; t < 64; ++t) {
+        w[t & 15] += small_sigma1(w[(t - 2) & 15]) + w[(t - 7) & 15] + small_sigma0(w[(t - 15) & 15]);
+        DM_ROUND(v, t, K[t] + w[t & 15]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += v[i];
+}
+
+__device__ __forceinline__ void unpack_be(uint32_t (&w)[16], const uint4 &a, const uint4 &b,
+                                          const uint4 &c, const uint4 &d)
+{
+    w[0] = bswap32(a.x);  w[1] = bswap32(a.y);  w[2] = bswap32(a.z);  w[3] = bswap32(a.w);
+    w[4] = bswap32(b.x);  w[5] = bswap32(b.y);  w[6] = bswap32(b.z);  w[7] = bswap32(b.w);
+    w[8] = bswap32(c.x);  w[9] = bswap32(c.y);  w[10] = bswap32(c.z); w[11] = bswap32(c.w);
+    w[12] = bswap32(d.x); w[13] = bswap32(d.y); w[14] = bswap32(d.z); w[15] = bswap32(d.w);
+}
+
+// Blob bytes are read exactly once: bypass L1 allocation, keep L2 default.
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// The last < 128 bytes of a run, as up to three "virtual" blocks: whole
+// blocks, then (FINAL only) the FIPS 180-4 §5.1.1 padding — a 0x80 byte
+// right after the message, zeros, and the 64-bit big-endian bit length in
+// the last two words of the last block.  Loads touch only 16-byte pieces
+// that hold at least one message byte.
+__device__ __forceinline__ void hash_tail(uint32_t (&s)[8], const uint8_t *src, uint8_t *dst,
+                                          uint32_t rem, bool final, uint64_t total_len, bool do_store)
+{
+    const uint32_t nvb = final ? ((rem + 72u) >> 6) : (rem >> 6);
+    const uint64_t bits = total_len << 3;
+#pragma unroll 1
+    for (uint32_t vb = 0; vb < nvb; ++vb) {
+        const uint32_t base = vb << 6;
+        uint32_t w[16];
+        uint4 q[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            q[g] = make_uint4(0u, 0u, 0u, 0u);
+            if (base + 16u * g < rem) {
+                q[g] = ld_stream(reinterpret_cast<const uint4 *>(src + base) + g);
+                if (dst != nullptr && do_store) st_stream(reinterpret_cast<uint4 *>(dst + base) + g, q[g]);
+            }
+        }
+        unpack_be(w, q[0], q[1], q[2], q[3]);
+        if (final) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int left = (int)rem - (int)(base + 4u * t);   // message bytes from this word on
+                if (left <= 0) w[t] = 0u;
+                else if (left < 4) w[t] &= 0xFFFFFFFFu << (32 - 8 * left);
+                if (left >= 0 && left < 4) w[t] |= 0x80u << (24 - 8 * left);
+            }
+            if (vb == nvb - 1) { w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
+        }
+        compress_regs(s, w);
+    }
+}
+
+__device__ __forceinline__ void load_state(uint32_t (&s)[8], const uint32_t *states, uint32_t slot, uint32_t flags)
+{
+    if (flags & JOB_INIT) {   // FIPS 180-4 §5.3.3
+        s[0] = 0x6a09e667u; s[1] = 0xbb67ae85u; s[2] = 0x3c6ef372u; s[3] = 0xa54ff53au;
+        s[4] = 0x510e527fu; s[5] = 0x9b05688cu; s[6] = 0x1f83d9abu; s[7] = 0x5be0cd19u;
+    } else {
+        const uint4 lo = *reinterpret_cast<const uint4 *>(states + 8ull * slot);
+        const uint4 hi = *reinterpret_cast<const uint4 *>(states + 8ull * slot + 4);
+        s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
+        s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+    }
+}
+
+__device__ __forceinline__ void store_state(const uint32_t (&s)[8], uint32_t *states, uint32_t *digests,
+                                            uint32_t slot, uint32_t flags)
+{
+    const uint4 lo = make_uint4(s[0], s[1], s[2], s[3]);
+    const uint4 hi = make_uint4(s[4], s[5], s[6], s[7]);
+    *reinterpret_cast<uint4 *>(states + 8ull * slot) = lo;
+    *reinterpret_cast<uint4 *>(states + 8ull * slot + 4) = hi;
+    if (flags & JOB_FINAL) {
+        *reinterpret_cast<uint4 *>(digests + 8ull * slot) = lo;
+        *reinterpret_cast<uint4 *>(digests + 8ull * slot + 4) = hi;
+    }
+}
+
+__device__ __forceinline__ HashJob load_job(const HashJob *jobs, uint32_t j)
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(jobs + j);
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    HashJob jb;
+    jb.src = reinterpret_cast<const uint8_t *>(((uint64_t)a.y << 32) | a.x);
+    jb.dst = reinterpret_cast<uint8_t *>(((uint64_t)a.w << 32) | a.z);
+    jb.nbytes = ((uint64_t)b.y << 32) | b.x;
+    jb.total_len = ((uint64_t)b.w << 32) | b.z;
+    const uint2 c = __ldg(reinterpret_cast<const uint2 *>(p + 2));
+    jb.slot = c.x; jb.flags = c.y; jb.pad_ = 0;
+    return jb;
+}
+
+// ---------------------------------------------------------------------------
+// wide: one lane per stream
+// ---------------------------------------------------------------------------
+constexpr int kWideThreads = 128;
+
+__global__ void __launch_bounds__(kWideThreads)
+sha256_wide_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *__restrict__ states,
+                   uint32_t *__restrict__ digests)
+{
+    const uint32_t j = blockIdx.x * kWideThreads + threadIdx.x;
+    if (j >= njobs) return;
+    const HashJob jb = load_job(jobs, j);
+    uint32_t s[8];
+    load_state(s, states, jb.slot, jb.flags);
+
+    const uint4 *p = reinterpret_cast<const uint4 *>(jb.src);
+    uint4 *q = reinterpret_cast<uint4 *>(jb.dst);
+    const bool copy = q != nullptr;
+    uint64_t npair = jb.nbytes >> 7;               // 128-byte lines
+#pragma unroll 1
+    for (; npair != 0; --npair) {
+        uint4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = ld_stream(p + i);
+        if (copy) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) st_stream(q + i, x[i]);
+            q += 8;
+        }
+        p += 8;
+        uint32_t w[16];
+        unpack_be(w, x[0], x[1], x[2], x[3]);
+        compress_regs(s, w);
+        unpack_be(w, x[4], x[5], x[6], x[7]);
+        compress_regs(s, w);
+    }
+    hash_tail(s, reinterpret_cast<const uint8_t *>(p), reinterpret_cast<uint8_t *>(q),
+              (uint32_t)(jb.nbytes & 127u), (jb.flags & JOB_FINAL) != 0, jb.total_len, true);
+    store_state(s, states, digests, jb.slot, jb.flags);
+}
+
+// ---------------------------------------------------------------------------
+// deep: one warp per stream
+// ---------------------------------------------------------------------------
+constexpr int kDeepWarps = 1;                 // warps per CTA; 1 lets the block scheduler
+                                              // spread few streams over all 592 sub-partitions
+constexpr int kKwStride = 68;                 // words per staged block: 64 + 4 pad -> conflict-free STS.128
+
+__global__ void __launch_bounds__(32 * kDeepWarps)
+sha256_deep_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *__restrict__ states,
+                   uint32_t *__restrict__ digests)
+{
+    __shared__ __align__(16) uint32_t kw_smem[kDeepWarps][32 * kKwStride];
+    constexpr uint32_t K[64] = {DM_K256_TABLE};
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t wid = threadIdx.x >> 5;
+    const uint32_t j = blockIdx.x * kDeepWarps + wid;
+    if (j >= njobs) return;
+    const HashJob jb = load_job(jobs, j);
+    uint32_t s[8];
+    load_state(s, states, jb.slot, jb.flags);
+    uint32_t *kw = kw_smem[wid];
+
+    const uint64_t nblk = jb.nbytes >> 6;
+    const uint64_t ngroups = (nblk + 31) >> 5;
+    const bool copy = jb.dst != nullptr;
+    const uint4 *p = reinterpret_cast<const uint4 *>(jb.src) + 4ull * lane;   // this lane's block in group 0
+    uint4 *q = reinterpret_cast<uint4 *>(jb.dst) + 4ull * lane;
+
+    uint4 x[4];
+    if (lane < nblk) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = ld_stream(p + i);
+    }
+#pragma unroll 1
+    for (uint64_t g = 0; g < ngroups; ++g) {
+        const uint64_t left = nblk - (g << 5);
+        const uint32_t nv = left < 32 ? (uint32_t)left : 32u;
+        // phase 1: every lane expands the schedule of its own block, K folded in
+        if (lane < nv) {
+            if (copy) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) st_stream(q + i, x[i]);
+            }
+            uint32_t w[16];
+            unpack_be(w, x[0], x[1], x[2], x[3]);
+            uint4 *out = reinterpret_cast<uint4 *>(kw + lane * kKwStride);
+#pragma unroll
+            for (int t = 0; t < 16; t += 4)
+                out[t >> 2] = make_uint4(w[t] + K[t], w[t + 1] + K[t + 1], w[t + 2] + K[t + 2], w[t + 3] + K[t + 3]);
+#pragma unroll
+            for (int t = 16; t < 64; t += 4) {
+#pragma unroll
+                for (int u = t; u < t + 4; ++u)
+                    w[u & 15] += small_sigma1(w[(u - 2) & 15]) + w[(u - 7) & 15] + small_sigma0(w[(u - 15) & 15]);
+                out[t >> 2] = make_uint4(w[t & 15] + K[t], w[(t + 1) & 15] + K[t + 1],
+                                         w[(t + 2) & 15] + K[t + 2], w[(t + 3) & 15] + K[t + 3]);
+            }
+        }
+        __syncwarp();
+        // prefetch the next group's block while the serial rounds run
+        p += 128; q += 128;
+        if (g + 1 < ngroups && lane < left - 32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = ld_stream(p + i);
+        }
+        // phase 2: the dependent chain, warp-uniform, one broadcast LDS.128 per 4 rounds
+#pragma unroll 1
+        for (uint32_t b = 0; b < nv; ++b) {
+            const uint4 *kp = reinterpret_cast<const uint4 *>(kw + b * kKwStride);
+            uint32_t v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = s[i];
+#pragma unroll
+            for (int t = 0; t < 64; t += 4) {
+                const uint4 k4 = kp[t >> 2];
+                DM_ROUND(v, t, k4.x);
+                DM_ROUND(v, t + 1, k4.y);
+                DM_ROUND(v, t + 2, k4.z);
+                DM_ROUND(v, t + 3, k4.w);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] += v[i];
+        }
+        __syncwarp();
+    }
+    const uint64_t done = nblk << 6;
+    hash_tail(s, jb.src + done, copy ? jb.dst + done : nullptr, (uint32_t)(jb.nbytes & 63u),
+              (jb.flags & JOB_FINAL) != 0, jb.total_len, lane == 0);
+    if (lane == 0) store_state(s, states, digests, jb.slot, jb.flags);
+}
+
+// ---------------------------------------------------------------------------
+// synthetic blob bytes
+// ---------------------------------------------------------------------------
+__global__ void synth_fill_kernel(uint64_t key, uint64_t byte_off, uint8_t *dst, size_t len)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    // fast path: generator words (8 B) and 16-byte stores line up
+    const bool fast = ((byte_off & 7) == 0) && (((uintptr_t)dst & 15) == 0);
+    const size_t nvec = fast ? (len >> 4) : 0;
+    const uint64_t w0 = byte_off >> 3;
+    ulonglong2 *v = reinterpret_cast<ulonglong2 *>(dst);
+    for (size_t i = tid; i < nvec; i += stride)
+        v[i] = make_ulonglong2(dm_blob_word_k(key, w0 + 2 * i), dm_blob_word_k(key, w0 + 2 * i + 1));
+    for (size_t i = (nvec << 4) + tid; i < len; i += stride) {
+        const uint64_t jx = byte_off + i;
+        dst[i] = (uint8_t)(dm_blob_word_k(key, jx >> 3) >> (8 * (jx & 7)));
+    }
+}
+
+// n blobs at ascending 16-byte-aligned offsets[] with lengths[]: one 16-byte
+// piece per thread iteration over the whole span, owner found by binary search.
+__global__ void synth_fill_many_kernel(uint64_t seed, uint64_t first_blob, uint8_t *base,
+                                       const uint64_t *__restrict__ offsets,
+                                       const uint64_t *__restrict__ lengths, uint32_t n,
+                                       uint64_t first_off, uint64_t span)
+{
+    const uint64_t nvec = (span + 15) >> 4;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t pos = first_off + (i << 4);
+        uint32_t lo = 0, hi = n;                       // offsets[lo] <= pos < offsets[hi]
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (offsets[mid] <= pos) lo = mid; else hi = mid;
+        }
+        const uint64_t in = pos - offsets[lo], len = lengths[lo];
+        if (in >= len) continue;                       // gap between blobs
+        const uint64_t key = dm_blob_key(seed, first_blob + lo);
+        const uint64_t a = dm_blob_word_k(key, in >> 3), b = dm_blob_word_k(key, (in >> 3) + 1);
+        if (in + 16 <= len) {
+            *reinterpret_cast<ulonglong2 *>(base + pos) = make_ulonglong2(a, b);
+        } else {
+            for (uint64_t k = 0; in + k < len; ++k)
+                base[pos + k] = (uint8_t)((k < 8 ? a : b) >> (8 * (k & 7)));
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_sha256_wide(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests,
+                               cudaStream_t stream)
+{
+    if (njobs == 0) return cudaSuccess;
+    const uint32_t grid = (njobs + kWideThreads - 1) / kWideThreads;
+    sha256_wide_kernel<<<grid, kWideThreads, 0, stream>>>(jobs, njobs, states, digests);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests,
+                               cudaStream_t stream)
+{
+    if (njobs == 0) return cudaSuccess;
+    const uint32_t grid = (njobs + kDeepWarps - 1) / kDeepWarps;
+    sha256_deep_kernel<<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_synth_fill(uint64_t seed, uint64_t blob, uint64_t byte_off, void *dst, size_t len,
+                              cudaStream_t stream)
+{
+    if (len == 0) return cudaSuccess;
+    size_t blocks = (len / 16 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    synth_fill_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dm_blob_key(seed, blob), byte_off,
+                                                            static_cast<uint8_t *>(dst), len);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_synth_fill_many(uint64_t seed, uint64_t first_blob, void *base, const uint64_t *dev_offsets,
+                                   const uint64_t *dev_lengths, uint32_t n, uint64_t first_off, uint64_t span,
+                                   cudaStream_t stream)
+{
+    if (n == 0 || span == 0) return cudaSuccess;
+    uint64_t blocks = (span / 16 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    synth_fill_many_kernel<<<(unsigned)blocks, 256, 0, stream>>>(seed, first_blob, static_cast<uint8_t *>(base),
+                                                                 dev_offsets, dev_lengths, n, first_off, span);
+    return cudaGetLastError();
+}
+
+}  // namespace dm

@@ -1,0 +1,186 @@
+/*
+ * demodel_b200.h — C-ABI of the B200 blob hash-and-cache engine.
+ *
+ * This is the drop-in boundary for demodel's cache path.  The reference
+ * (moeru-ai/demodel @ fb8342aa) has no FFI, plugin or C interface of its own
+ * (/root/reference/pkg/utils/fs.go:1-8 is all of pkg/), so
+ * each entry point below cites the reference *hook* whose body it serves:
+ *
+ *   OnResponse hook  cmd/demodel/start.go:201-204   (today: Println, return resp)
+ *       -> a Go io.ReadCloser wrapped around resp.Body calls
+ *          dm_stream_open / dm_stream_write (or acquire+commit) /
+ *          dm_stream_finish / dm_stream_abort        — "hash while copying
+ *          into the cache".
+ *   OnRequest hook   cmd/demodel/start.go:197-200   (today: Println, return req,nil)
+ *       -> dm_cache_open / dm_cache_read / dm_cache_close build the
+ *          *http.Response that short-circuits upstream — "serve a cache hit".
+ *   start()          cmd/demodel/start.go:167-216
+ *       -> dm_engine_create once per GPU before net.Listen (start.go:206),
+ *          dm_engine_destroy on shutdown; dm_shard_of picks the engine.
+ *
+ * The cgo binding a maintainer would add is in INTEGRATION.md and go/.
+ *
+ * Conventions: plain C types only (no CUDA / torch types).  Every function is
+ * thread-safe: net/http runs one goroutine per connection (start.go:210-215)
+ * and cgo enters from many OS threads.  Functions return DM_OK (0) or a
+ * negative dm_err; they never abort, throw or call exit.  There is NO CPU
+ * fallback: without a usable CUDA device dm_engine_create fails with
+ * DM_ENODEV / DM_ECUDA and nothing else can be called.
+ */
+#ifndef DEMODEL_B200_H
+#define DEMODEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM_ABI_VERSION 1u
+
+typedef enum dm_err {
+    DM_OK        = 0,
+    DM_EINVAL    = -1,   /* bad argument / unknown id */
+    DM_ENOMEM    = -2,   /* HBM arena, pinned ring or stream table exhausted */
+    DM_ENOENT    = -3,   /* digest not in the content-addressed store */
+    DM_ECUDA     = -4,   /* CUDA runtime error; dm_last_error() has the text */
+    DM_ESTATE    = -5,   /* call not valid in the stream's current state */
+    DM_EIO       = -6,   /* on-disk CAS tier I/O error */
+    DM_ENODEV    = -7,   /* no CUDA device / device ordinal out of range */
+    DM_ERANGE    = -8    /* offset beyond blob end */
+} dm_err;
+
+typedef struct dm_engine dm_engine;   /* opaque; owned by caller between create/destroy */
+
+/* dm_config.flags */
+#define DM_F_NO_HBM_CAS   0x1u  /* hash + verify only; bytes are not retained in HBM */
+#define DM_F_DISK_SYNC    0x2u  /* dm_stream_finish returns only after the disk tier holds the blob */
+
+typedef struct dm_config {
+    uint32_t struct_size;     /* = sizeof(dm_config); ABI guard */
+    int32_t  device;          /* CUDA ordinal; one engine per GPU */
+    uint64_t hbm_cas_bytes;   /* HBM arena for the content-addressed store; 0 = 1/2 of free HBM */
+    uint64_t ring_bytes;      /* pinned host ring; 0 = 256 MiB */
+    uint32_t slab_bytes;      /* ring slab = one H2D DMA; multiple of 256; 0 = 1 MiB */
+    uint32_t max_streams;     /* concurrently open streams; 0 = 65536 */
+    const char *cas_dir;      /* on-disk tier root, NULL = HBM tier only */
+    uint32_t flags;
+    uint32_t reserved;
+} dm_config;
+
+typedef struct dm_stats {
+    uint64_t bytes_ingested;      /* through dm_stream_write/commit */
+    uint64_t bytes_hashed;        /* by the SHA-256 kernels */
+    uint64_t bytes_served;        /* through dm_cache_read */
+    uint64_t blobs_committed;
+    uint64_t blobs_mismatched;
+    uint64_t kernel_launches;     /* SHA-256 kernel launches (wide + deep) */
+    uint64_t launches_wide;
+    uint64_t launches_deep;
+    double   kernel_ms;           /* CUDA-event time summed over those launches */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    uint64_t hbm_cas_used;
+    uint64_t hbm_cas_capacity;
+    uint64_t open_streams;
+} dm_stats;
+
+/* ---- engine lifetime (start.go:167-216) -------------------------------- */
+uint32_t    dm_abi_version(void);
+int         dm_device_count(void);                       /* <0: dm_err */
+int         dm_engine_create(const dm_config *cfg, dm_engine **out);
+void        dm_engine_destroy(dm_engine *e);
+int         dm_engine_stats(dm_engine *e, dm_stats *out);
+const char *dm_strerror(int err);
+const char *dm_last_error(void);                         /* thread-local detail text */
+
+/* Digest-prefix sharding: which of n_shards engines owns a
+ * blob.  Uses the leading 16 bits so any n_shards (not only powers of two)
+ * splits the digest space evenly; for n = 2,4,8 it equals digest[0] >> (8-log2 n). */
+uint32_t    dm_shard_of(const uint8_t digest[32], uint32_t n_shards);
+
+/* ---- ingest: OnResponse body tee (start.go:201-204) -------------------- */
+/* expect: the LFS oid / OCI layer digest known from the URL, or NULL.
+ * size_hint: Content-Length, or 0 when unknown (chunked). */
+int dm_stream_open(dm_engine *e, const uint8_t expect[32], uint64_t size_hint, uint64_t *id);
+/* Copies buf before returning (the Go caller reuses its 32 KiB io.Copy
+ * buffer on the next Read).  Blocks only for ring back-pressure. */
+int dm_stream_write(dm_engine *e, uint64_t id, const void *buf, size_t len);
+/* Zero-copy variant: borrow a window of the pinned ring, Read() into it,
+ * then commit the bytes actually read.  At most one outstanding window per
+ * stream; *cap >= 1 on success. */
+int dm_stream_acquire(dm_engine *e, uint64_t id, void **ptr, size_t *cap);
+int dm_stream_commit(dm_engine *e, uint64_t id, size_t len);
+/* Blocks until every byte is hashed.  digest_out receives the SHA-256 of
+ * the bytes written.  *matched = 1 if expect was NULL or equals the digest
+ * (the blob is then published in the CAS under digest_out), 0 otherwise (the
+ * bytes are discarded).  The id is released either way. */
+int dm_stream_finish(dm_engine *e, uint64_t id, uint8_t digest_out[32], int *matched);
+/* Upstream error / client went away: drop the partial blob, release the id. */
+int dm_stream_abort(dm_engine *e, uint64_t id);
+
+/* ---- hit serving: OnRequest short-circuit (start.go:197-200) ----------- */
+int dm_cache_contains(dm_engine *e, const uint8_t digest[32], uint64_t *size);  /* DM_ENOENT on miss */
+int dm_cache_open(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size);
+int dm_cache_read(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t len, size_t *nread);
+int dm_cache_close(dm_engine *e, uint64_t reader);
+int dm_cache_evict(dm_engine *e, const uint8_t digest[32]);   /* HBM tier only; disk copy stays */
+
+/* ---- device-resident ingest -------------------------------------------- */
+/* Hash-and-cache n blobs whose bytes are ALREADY in this GPU's HBM (landed
+ * by GPUDirect, produced on device, or the bench's "inputs resident" leg).
+ * Blob i occupies [dev_base + offsets[i], dev_base + offsets[i] + lengths[i]);
+ * every offsets[i] must be a multiple of 16 and the blobs must not overlap.
+ * expect (n*32 bytes) may be NULL.
+ * One fused kernel pass reads each byte once, advances its blob's SHA-256
+ * state and writes the byte into the blob's CAS extent.  digests_out gets
+ * n*32 bytes; matched_out (n bytes, optional) the per-blob verdicts.
+ * kernel_ms (optional) = CUDA-event time of the hash launches on the
+ * engine's own stream.  flags: DM_ING_* below. */
+#define DM_ING_HASH_ONLY   0x1u   /* do not copy into the CAS (1 B/B of traffic instead of 2) */
+#define DM_ING_REPLACE     0x2u   /* evict an existing blob with the same digest first (benchmarks) */
+#define DM_ING_FORCE_WIDE  0x4u   /* kernel selection override: lane-per-stream */
+#define DM_ING_FORCE_DEEP  0x8u   /* kernel selection override: warp-per-stream */
+int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets,
+                     const uint64_t *lengths, uint32_t n, const uint8_t *expect, uint8_t *digests_out, uint8_t *matched_out,
+                     uint32_t flags, double *kernel_ms);
+
+/* Device pointer + extent walk of a cached blob, for consumers that want the
+ * bytes in HBM (e.g. a weight loader on the same GPU).  Returns the number
+ * of extents; fills up to max_ext (dev_ptr, len) pairs. */
+int dm_cache_device_extents(dm_engine *e, uint64_t reader, void **dev_ptrs, uint64_t *lens, uint32_t max_ext);
+
+/* ---- synthetic blob bytes ------------------------------ */
+/* Counter-based generator: byte j of blob `blob` under `seed` is a pure
+ * function of (seed, blob, j); host and device versions agree bit for bit. */
+void dm_synth_fill_host(uint64_t seed, uint64_t blob, uint64_t byte_off, void *dst, size_t len);
+int  dm_synth_fill_device(dm_engine *e, uint64_t seed, uint64_t blob, uint64_t byte_off,
+                          void *dev_dst, size_t len);
+/* Fill n blobs laid out by offsets[]/lengths[] (as in dm_ingest_device, offsets
+ * ascending) in one launch; blob i gets generator index first_blob + i. */
+int  dm_synth_fill_device_many(dm_engine *e, uint64_t seed, uint64_t first_blob, void *dev_base,
+                               const uint64_t *offsets, const uint64_t *lengths, uint32_t n);
+
+/* ---- proxy-side driver (the host half of the path, in-process) --------- */
+/* What the Go side does per connection, restated in C++ threads so the
+ * end-to-end path can be driven here, where no Go toolchain exists:
+ * `nthreads` connection workers each pull whole blobs from a shared queue,
+ * read them in `chunk`-byte pieces from caller-owned HOST memory
+ * [host_base + offsets[i], host_base + offsets[i+1]) and push them through
+ * dm_stream_open/write/finish (zero_copy != 0: acquire/commit with the
+ * "socket read" landing directly in the ring).  Streams are interleaved
+ * `concurrency` at a time the way concurrent goroutines would be.
+ * Returns wall seconds in *seconds. */
+int dm_proxy_drive(dm_engine *e, const void *host_base, const uint64_t *offsets, uint32_t n,
+                   const uint8_t *expect, size_t chunk, uint32_t concurrency, int nthreads,
+                   int zero_copy, uint8_t *digests_out, uint8_t *matched_out, double *seconds);
+/* Serve n cached blobs back out into caller-owned host memory in `chunk`
+ * pieces (the cache-hit path), `nthreads` readers. */
+int dm_proxy_serve(dm_engine *e, const uint8_t *digests, uint32_t n, void *host_base,
+                   const uint64_t *offsets, size_t chunk, int nthreads, double *seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEMODEL_B200_H */

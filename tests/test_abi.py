@@ -1,0 +1,83 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol the
+header declares, and refuses (loudly) to run the hash path without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import demodel_b200
+from demodel_b200 import _lib
+from demodel_b200.shard import owner_of
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "demodel_b200.h")
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = demodel_b200.load()
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/demodel_b200.h but not exported"
+    # and the ctypes table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_abi_version_and_struct_layout():
+    lib = demodel_b200.load()
+    assert lib.dm_abi_version() == 1
+    assert C.sizeof(_lib.DmConfig) == 48        # matches the C layout on LP64
+    assert C.sizeof(_lib.DmStats) == 14 * 8
+
+
+def test_strerror_covers_all_codes():
+    lib = demodel_b200.load()
+    seen = {lib.dm_strerror(c).decode() for c in range(0, -9, -1)}
+    assert len(seen) == 9 and "unknown error" not in seen
+    assert lib.dm_strerror(-99).decode() == "unknown error"
+
+
+def test_shard_of_matches_python_router():
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 4, 8, 7):
+        for _ in range(200):
+            d = rng.integers(0, 256, size=32, dtype=np.uint8).tobytes()
+            assert demodel_b200.shard_of(d, n) == owner_of(d, n)
+    # powers of two reduce to the leading bits of digest[0]
+    for b in range(256):
+        d = bytes([b]) + bytes(31)
+        assert demodel_b200.shard_of(d, 4) == b >> 6
+        assert demodel_b200.shard_of(d, 8) == b >> 5
+
+
+def test_rejects_bad_config():
+    lib = demodel_b200.load()
+    cfg = _lib.DmConfig()
+    cfg.struct_size = 4                           # wrong ABI guard
+    h = C.c_void_p()
+    assert lib.dm_engine_create(C.byref(cfg), C.byref(h)) == _lib.DM_EINVAL
+    assert not h.value
+
+
+def test_no_cpu_fallback_without_a_device():
+    lib = demodel_b200.load()
+    if lib.dm_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(demodel_b200.DmError) as ei:
+        demodel_b200.Engine(device=0, hbm_cas_bytes=1 << 20)
+    assert ei.value.code == demodel_b200.DM_ENODEV
+
+
+def test_product_generator_matches_oracle_generator(oracle):
+    # host half of the synthetic-bytes generator (pure CPU, no device needed)
+    seed = 0xDE40DE1
+    for blob, off, n in [(0, 0, 4096), (3, 5, 1000), (9, 8, 64), (2, 1 << 33, 777), (1, 123457, 33)]:
+        assert np.array_equal(demodel_b200.synth_fill_host(seed, blob, off, n), oracle.blob(seed, blob, off, n))
