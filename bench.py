@@ -1,0 +1,389 @@
+#!/usr/bin/env python3
+"""bench.py — blob hash-and-cache throughput (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of synthetic blobs.
+
+  value     whole-job GB/s with the blobs already resident in HBM: one fused
+            multi-buffer SHA-256 pass (dm_ingest_device) that reads every byte
+            once, advances its blob's digest and writes it into the CAS.
+  e2e       the same blobs pushed from HOST memory through the C-ABI the proxy
+            would call (dm_proxy_drive -> dm_stream_open/write/finish): ring
+            memcpy, H2D DMA, hash, digest read-back, all inside the timed region.
+  roofline  the SHA-256 kernel: algorithmic bytes (2 B per blob byte for
+            hash-and-cache) / CUDA-event kernel time, against the measured HBM
+            copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference
+            the hash-and-cache loop north_star attributes to the reference,
+            timed on this box's host cores (oracle/cpu_baseline.c: OpenSSL
+            EVP_sha256 + memcpy, a stand-in for Go crypto/sha256 — Go is not
+            installed and the reference holds no such loop).
+
+Multi-GPU: one process per GPU under torchrun; blobs are partitioned by the
+production routing function (URL-hash for blobs whose digest is not known up
+front), per-GPU work is fixed (weak scaling), no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 0xDE40DE1
+METRIC = "blob hash-and-cache throughput"
+UNIT = "GB/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: 256 concurrent 64 MB HF LFS range streams on 1 B200
+    "hf_lfs_256x64MiB": {"sizes": [64 << 20] * 256, "baseline_config": 2},
+    # BASELINE.json configs[1]: Llama-3-8B safetensors shard set (real shard sizes)
+    "llama3_8b_shards": {"sizes": [4976698672, 4999802720, 4915916176, 1168138808], "baseline_config": 1},
+    # kernel saturation probe (not a BASELINE config): enough streams to fill every sub-partition
+    # 148 SMs x 4 sub-partitions x 8 warps x 32 lanes = 151552 streams
+    "saturate_151552x112KiB": {"sizes": [112 << 10] * 151552, "baseline_config": None},
+    "tiny": {"sizes": [1 << 20] * 64, "baseline_config": None},
+}
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _cpu_quota():
+    try:
+        q, p_ = open("/sys/fs/cgroup/cpu.max").read().split()
+        return None if q == "max" else float(q) / float(p_)
+    except Exception:
+        return None
+
+
+def _layout(sizes):
+    offs, pos = [], 0
+    for s in sizes:
+        offs.append(pos)
+        pos += (s + 255) // 256 * 256
+    return offs, pos
+
+
+def _my_blob_indices(n_blobs, rank, world):
+    """Disjoint per-rank blob sets chosen by the production router: synthetic
+    blobs have no digest before they are hashed, so they are homed by URL hash
+    (demodel_b200.shard.owner_of_url), the rule for unknown-digest blobs."""
+    from demodel_b200.shard import owner_of_url
+    if world == 1:
+        return list(range(n_blobs))
+    out, k = [], 0
+    while len(out) < n_blobs:
+        if owner_of_url(f"synthetic://blob/{k}", world) == rank:
+            out.append(k)
+        k += 1
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank, world):
+    """The CPU arm: OpenSSL hash-and-cache loop on all host threads."""
+    if rank != 0:
+        return
+    import numpy as np
+    from tests import _oracle
+    orc = _oracle.load()
+    sizes = WORKLOADS[args.workload]["sizes"]
+    ncpu = os.cpu_count() or 1
+    threads = min(ncpu, len(sizes))
+    # bounded sample: whole blobs, at most ~16 GiB so K steps stay within minutes
+    budget, take, tot = 16 << 30, 0, 0
+    while take < len(sizes) and (take == 0 or tot + sizes[take] <= budget):
+        tot += sizes[take]; take += 1
+    sizes = sizes[:take]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    src = np.empty(int(off[-1]), dtype=np.uint8)
+    import demodel_b200  # product generator (CPU half), only to make the bytes
+    lib = demodel_b200.load()
+    import ctypes as C
+
+    def fill(i):
+        lib.dm_synth_fill_host(SEED, i, 0, C.c_void_p(src.ctypes.data + int(off[i])), sizes[i])
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(ncpu, 64)) as ex:
+        list(ex.map(fill, range(len(sizes))))
+    cache = np.empty_like(src)
+    total = int(off[-1])
+    for _ in range(args.warmup):
+        orc.hash_and_cache(src, off, chunk=32768, threads=threads, cache=cache)
+    t = 0.0
+    for _ in range(args.steps):
+        secs, digs = orc.hash_and_cache(src, off, chunk=32768, threads=threads, cache=cache)
+        t += secs
+    gbs = total * args.steps / t / 1e9
+    sample = f"{len(sizes)} of {len(WORKLOADS[args.workload]['sizes'])} blobs, {total} B per step, 32 KiB updates + memcpy into an in-memory cache"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": args.workload, "blobs": len(sizes), "bytes_per_step": total,
+                   "note": "OpenSSL EVP_sha256 stand-in for Go crypto/sha256 (no Go toolchain; reference has no such loop)"},
+        "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hf_lfs_256x64MiB")
+    ap.add_argument("--kernel", default=None, choices=[None, "wide", "deep"])
+    ap.add_argument("--hash-only", action="store_true", help="value leg without the fused CAS copy (1 B/B)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-zero-copy", action="store_true")
+    ap.add_argument("--blobs", type=int, default=0, help="override: number of blobs (with --blob-bytes)")
+    ap.add_argument("--blob-bytes", type=int, default=0)
+    args = ap.parse_args()
+    if args.blobs and args.blob_bytes:
+        args.workload = f"custom_{args.blobs}x{args.blob_bytes}"
+        WORKLOADS[args.workload] = {"sizes": [args.blob_bytes] * args.blobs, "baseline_config": None}
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import demodel_b200
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback on the hash path)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sizes = WORKLOADS[args.workload]["sizes"]
+    n = len(sizes)
+    offs, span = _layout(sizes)
+    total = sum(sizes)
+    mine = _my_blob_indices(n, rank, world)
+    hbm_peak, peak_src = _peaks()
+
+    cas_bytes = 0 if args.hash_only else span + (64 << 20)
+    eng = demodel_b200.Engine(device=local, hbm_cas_bytes=max(cas_bytes, 256 << 20) + (2 << 30), ring_bytes=1 << 30,
+                              slab_bytes=1 << 20, max_streams=max(65536, n + 1024))
+    dev = torch.empty(span, dtype=torch.uint8, device=f"cuda:{local}")
+    # blob indices are consecutive per rank only when world == 1; fill one by one otherwise
+    if mine == list(range(mine[0], mine[0] + n)):
+        eng.synth_fill_device_many(SEED, mine[0], dev.data_ptr(), offs, sizes)
+    else:
+        for i, k in enumerate(mine):
+            eng.synth_fill_device(SEED, k, 0, dev.data_ptr() + offs[i], sizes[i])
+    torch.cuda.synchronize()
+
+    # ---- value leg: inputs resident in HBM --------------------------------------------
+    digs, _, _ = eng.ingest_device(dev.data_ptr(), offs, sizes, hash_only=True, kernel=args.kernel)   # learn the oids
+    expect = b"".join(digs)
+    expect_arr = np.frombuffer(expect, dtype=np.uint8)
+
+    def step():
+        return eng.ingest_device(dev.data_ptr(), offs, sizes, expect=expect, hash_only=args.hash_only,
+                                 replace=not args.hash_only, kernel=args.kernel, raw=True)
+
+    for _ in range(args.warmup):
+        d, m, _ = step()
+        assert np.array_equal(d, expect_arr) and m.all()
+    s0 = eng.stats()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    kernel_ms = 0.0
+    for _ in range(args.steps):
+        d, m, ms = step()
+        kernel_ms += ms
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    s1 = eng.stats()
+    assert np.array_equal(d, expect_arr) and m.all()
+    launches = int(s1["kernel_launches"] - s0["kernel_launches"])
+
+    tt = torch.tensor([wall, kernel_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    wall_max, kernel_ms_max = float(tt[0]), float(tt[1])
+    value = total * world * args.steps / wall_max / 1e9
+    bytes_per_blob_byte = 1 if args.hash_only else 2
+    achieved = bytes_per_blob_byte * total * args.steps / (kernel_ms_max / 1e3) / 1e9
+
+    # spot check against an independent implementation on the host (hashlib), outside the timed region
+    import hashlib
+    probe = min(range(n), key=lambda i: sizes[i])
+    host_probe = dev[offs[probe]:offs[probe] + sizes[probe]].cpu().numpy()
+    assert hashlib.sha256(host_probe.tobytes()).digest() == digs[probe], "GPU digest differs from hashlib"
+
+    # ---- e2e leg: host buffers through the proxy-facing C-ABI ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        hoff = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+        host = np.empty(int(hoff[-1]), dtype=np.uint8)
+        for i in range(n):   # D2H of the same bytes the value leg hashed (setup, untimed)
+            host[int(hoff[i]):int(hoff[i + 1])] = dev[offs[i]:offs[i] + sizes[i]].cpu().numpy()
+        for d_ in digs:
+            eng.cache_evict(d_)
+        conc = min(n, 256)
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(1):
+            dd, mm, _ = eng.proxy_drive(host, hoff, expect=expect, chunk=32768, concurrency=conc,
+                                        zero_copy=args.e2e_zero_copy)
+            assert dd == digs and all(mm)
+            for d_ in digs:
+                eng.cache_evict(d_)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            dd, mm, _ = eng.proxy_drive(host, hoff, expect=expect, chunk=32768, concurrency=conc,
+                                        zero_copy=args.e2e_zero_copy)
+            for d_ in digs:
+                eng.cache_evict(d_)
+        barrier()
+        e_wall = time.perf_counter() - t0
+        assert dd == digs and all(mm)
+        te = torch.tensor([e_wall], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": total * world * e2e_steps / float(te[0]) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": total, "d2h_bytes_per_step": 32 * n, "steps": e2e_steps,
+               "api": "dm_proxy_drive -> dm_stream_open/write/finish, 32 KiB writes, %d connection threads%s"
+                      % (conc, ", zero-copy ring windows" if args.e2e_zero_copy else "")}
+        del host
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) -----------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from tests import _oracle
+        orc = _oracle.load()
+        take = 0
+        tot = 0
+        while take < n and (take == 0 or tot + sizes[take] <= (16 << 30)):
+            tot += sizes[take]; take += 1
+        coff = np.concatenate([[0], np.cumsum(sizes[:take])]).astype(np.uint64)
+        src = np.empty(int(coff[-1]), dtype=np.uint8)
+        for i in range(take):
+            src[int(coff[i]):int(coff[i + 1])] = dev[offs[i]:offs[i] + sizes[i]].cpu().numpy()
+        cache = np.empty_like(src)
+        threads = min(os.cpu_count() or 1, take)
+        orc.hash_and_cache(src, coff, chunk=32768, threads=threads, cache=cache)          # warm
+        secs, cd = orc.hash_and_cache(src, coff, chunk=32768, threads=threads, cache=cache)
+        assert cd == digs[:take], "CPU arm and GPU digests differ"
+        secs1, _ = orc.hash_and_cache(src, coff[:2], chunk=32768, threads=1, cache=cache)
+        cpu = {"value": tot / secs / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{take} of {n} blobs ({tot} B), OpenSSL EVP_sha256 32 KiB updates + memcpy to an in-memory cache "
+                         f"(stand-in for Go crypto/sha256)",
+               "single_core_gbs": sizes[0] / secs1 / 1e9, "host_cpus": os.cpu_count()}
+        del src, cache
+
+    if rank == 0:
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": args.workload, "baseline_config": WORKLOADS[args.workload]["baseline_config"],
+                       "blobs_per_gpu": n, "bytes_per_gpu_per_step": total, "mode": "hash-only" if args.hash_only else "hash-and-cache (fused CAS copy)",
+                       "kernel": args.kernel or ("deep" if n < 1024 else "wide"), "seed": hex(SEED),
+                       "l2": "inputs (%.1f GB) larger than L2 (126 MB); no flush needed" % (total / 1e9),
+                       "parallelism": f"shard{world} (URL-hash homed, no collective)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_blob_byte": bytes_per_blob_byte, "kernel_ms_per_step": kernel_ms_max / args.steps},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "host": {"cpus": os.cpu_count(), "cpu_quota": _cpu_quota(), "kernel_variant": os.environ.get("DM_KERNEL_VARIANT")},
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -67,7 +68,9 @@ int fail_cuda(cudaError_t err, const char *where)
 
 constexpr uint64_t kAlign = 256;           // CAS extent granularity
 constexpr uint64_t kMaxGrow = 256ull << 20;
-constexpr int kCycles = 4;                 // pump launches in flight
+constexpr int kCycles = 2;                 // hash launch descriptors (one in flight, one being built)
+constexpr int kSlabBatches = 64;           // groups of DMA'd slabs waiting for their copy events
+constexpr int kStripes = 64;               // stream-table lock stripes
 constexpr int kCopyStreams = 2;
 constexpr size_t kBounceBytes = 4u << 20;
 constexpr int kBounces = 8;
@@ -172,7 +175,7 @@ struct Stream {
     Slab *cur = nullptr;
     uint32_t cur_fill = 0;
     bool window_out = false;   // acquire() window outstanding
-    bool dirty = false;        // queued for the pump
+    bool queued = false;       // in the pump's inbox / ready list (guarded by mu)
     bool final_issued = false;
     uint32_t jobs_inflight = 0;
     St st = St::Open;
@@ -197,10 +200,14 @@ struct Cycle {
     uint32_t njobs = 0;
     bool deep = false;
     uint64_t bytes = 0;
-    bool slabs_released = false;
-    std::vector<Slab *> slabs;
     std::vector<std::shared_ptr<Stream>> streams;   // one entry per job
     std::vector<uint8_t> is_final;
+};
+
+struct SlabBatch {
+    bool busy = false;
+    cudaEvent_t ev[kCopyStreams]{};
+    std::vector<Slab *> slabs;
 };
 
 struct Bounce { uint8_t *host = nullptr; cudaStream_t stream{}; };
@@ -212,6 +219,7 @@ struct dm_engine {
     std::string cas_dir;
     int device = 0;
     int sm_count = 148;
+    int variant_wide = dm::kDefaultWideVariant, variant_deep = dm::kDefaultDeepVariant;   // DM_KERNEL_VARIANT overrides (tuning only)
 
     cudaStream_t copy_stream[kCopyStreams]{};
     cudaStream_t hash_stream{}, ingest_stream{}, util_stream{};
@@ -230,8 +238,10 @@ struct dm_engine {
     uint32_t *h_digests = nullptr;   // mapped pinned, [max_streams][8]
     uint32_t *d_digests = nullptr;   // device alias of h_digests
 
-    std::mutex mu;                   // streams / blobs / readers / slots
-    std::unordered_map<uint64_t, std::shared_ptr<Stream>> streams;
+    std::mutex mu;                   // blobs / readers / slots
+    std::mutex stripe_mu[kStripes];  // stream table, striped by id: dm_stream_write never takes `mu`
+    std::unordered_map<uint64_t, std::shared_ptr<Stream>> streams[kStripes];
+    std::atomic<uint64_t> n_streams{0};
     std::vector<uint32_t> free_slots;
     uint64_t next_id = 1;
     std::unordered_map<Digest, std::shared_ptr<Blob>, DigestHash> blobs;
@@ -245,6 +255,7 @@ struct dm_engine {
     bool stop = false;
     std::thread pump;
     Cycle cycles[kCycles];
+    SlabBatch batches[kSlabBatches];
     uint32_t max_jobs = 0;
 
     std::mutex spill_mu;
@@ -411,12 +422,15 @@ int take_slab(dm_engine *e, Stream *s, std::unique_lock<std::mutex> &g)
     return DM_OK;
 }
 
+// Tell the pump this stream has new DMA'd bytes (or is finishing).  Stream mutex held.
 void mark_dirty(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *submitted)
 {
+    const bool enqueue = !sp->queued;
+    sp->queued = true;
     {
         std::lock_guard<std::mutex> g(e->work_mu);
         if (submitted) e->pending_slabs.push_back(submitted);
-        if (!sp->dirty) { sp->dirty = true; e->dirty.push_back(sp); }
+        if (enqueue) e->dirty.push_back(sp);
     }
     e->work_cv.notify_one();
 }
@@ -430,6 +444,7 @@ int submit_slab(dm_engine *e, const std::shared_ptr<Stream> &sp)
     const uint32_t n = s->cur_fill;
     s->cur = nullptr; s->cur_fill = 0;
     if (n == 0) { slab_put(e, slab); return DM_OK; }
+    cudaSetDevice(e->device);       // the caller may be any OS thread (cgo)
     int rc = ensure_capacity(e, s, s->dma_issued + n);
     if (rc != DM_OK) { slab_put(e, slab); return rc; }
     cudaStream_t cs = e->copy_stream[s->id % kCopyStreams];
@@ -549,7 +564,6 @@ void reap_cycle(dm_engine *e, Cycle &c)
         std::lock_guard<std::mutex> g(e->stat_mu);
         e->st_kernel_ms += ms;
     }
-    if (!c.slabs_released) { for (Slab *s : c.slabs) slab_put(e, s); c.slabs.clear(); c.slabs_released = true; }
     e->st_hashed += c.bytes;
     for (size_t i = 0; i < c.streams.size(); ++i) {
         std::shared_ptr<Stream> &sp = c.streams[i];
@@ -571,26 +585,21 @@ void reap_cycle(dm_engine *e, Cycle &c)
     c.njobs = 0; c.bytes = 0; c.busy = false;
 }
 
-// Returns true if anything was launched or recorded.
-bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &work, std::vector<Slab *> &slabs)
+// Build one job per ready stream and launch ONE multi-buffer kernel over them.
+// Streams that still have unhashed bytes afterwards stay in `ready`.
+bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &ready)
 {
-    c.slabs.swap(slabs);
-    c.slabs_released = false;
     c.njobs = 0; c.bytes = 0;
-    const uint64_t quantum = (uint64_t)e->cfg.slab_bytes * 4;   // bounds one launch's longest lane
+    const uint64_t quantum = (uint64_t)e->cfg.slab_bytes * 2;   // bounds one launch's longest lane
     std::vector<std::shared_ptr<Stream>> again;
-    for (auto &sp : work) {
+    for (auto &sp : ready) {
         Stream *s = sp.get();
         std::lock_guard<std::mutex> g(s->mu);
-        {
-            std::lock_guard<std::mutex> gw(e->work_mu);
-            s->dirty = false;
-        }
-        if (s->st == St::Aborted || s->st == St::Done || s->final_issued) continue;
+        if (s->st == St::Aborted || s->st == St::Done || s->final_issued) { s->queued = false; continue; }
         if (c.njobs >= e->max_jobs) { again.push_back(sp); continue; }
         const bool finishing = s->st == St::Finishing;
         uint64_t n = finishing ? (s->received - s->hash_issued) : ((s->dma_issued - s->hash_issued) & ~63ull);
-        if (!finishing && n == 0) continue;
+        if (!finishing && n == 0) { s->queued = false; continue; }
         uint64_t contig = 0;
         uint8_t *src = n ? seg_at(e, s->extents, s->hash_issued, &contig) : nullptr;
         bool final = finishing;
@@ -599,7 +608,7 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &wor
         dm::HashJob &jb = c.h_jobs[c.njobs++];
         jb.src = src; jb.dst = nullptr; jb.nbytes = n; jb.total_len = s->received; jb.slot = s->slot;
         jb.flags = (s->hash_issued == 0 ? dm::JOB_INIT : 0u) | (final ? dm::JOB_FINAL : 0u);
-        jb.pad_ = 0;
+        jb.one = 1; jb.pad_ = 0;
         s->hash_issued += n;
         s->jobs_inflight++;
         if (final) s->final_issued = true;
@@ -607,80 +616,95 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &wor
         c.streams.push_back(sp);
         c.is_final.push_back(final ? 1 : 0);
         if (!final && (finishing || ((s->dma_issued - s->hash_issued) & ~63ull))) again.push_back(sp);
+        else s->queued = false;
     }
-    work.clear();
-    if (!again.empty()) {
-        std::lock_guard<std::mutex> gw(e->work_mu);
-        for (auto &sp : again)
-            if (!sp->dirty) { sp->dirty = true; e->dirty.push_back(sp); }
-    }
-    if (c.njobs == 0 && c.slabs.empty()) return false;
+    ready.swap(again);
+    if (c.njobs == 0) return false;
 
     // Everything whose DMA was enqueued before this point is covered by these events.
     for (int i = 0; i < kCopyStreams; ++i) {
         cudaEventRecord(c.copy_ev[i], e->copy_stream[i]);
         cudaStreamWaitEvent(e->hash_stream, c.copy_ev[i], 0);
     }
-    if (c.njobs) {
-        c.deep = c.njobs < dm::kDeepWideCrossover;
-        if (!c.deep) {
-            // lanes of a warp run in lock step: keep neighbours the same length
-            std::vector<uint32_t> order(c.njobs);
-            for (uint32_t i = 0; i < c.njobs; ++i) order[i] = i;
-            std::stable_sort(order.begin(), order.end(),
-                             [&](uint32_t a, uint32_t b) { return c.h_jobs[a].nbytes > c.h_jobs[b].nbytes; });
-            std::vector<dm::HashJob> tmp(c.h_jobs, c.h_jobs + c.njobs);
-            std::vector<std::shared_ptr<Stream>> st2(c.njobs);
-            std::vector<uint8_t> fin2(c.njobs);
-            for (uint32_t i = 0; i < c.njobs; ++i) { c.h_jobs[i] = tmp[order[i]]; st2[i] = c.streams[order[i]]; fin2[i] = c.is_final[order[i]]; }
-            c.streams.swap(st2); c.is_final.swap(fin2);
-        }
-        cudaMemcpyAsync(c.d_jobs, c.h_jobs, sizeof(dm::HashJob) * c.njobs, cudaMemcpyHostToDevice, e->hash_stream);
-        cudaEventRecord(c.k_start, e->hash_stream);
-        if (c.deep) { dm::launch_sha256_deep(c.d_jobs, c.njobs, e->d_states, e->d_digests, e->hash_stream); e->st_deep++; }
-        else { dm::launch_sha256_wide(c.d_jobs, c.njobs, e->d_states, e->d_digests, e->hash_stream); e->st_wide++; }
-        e->st_launches++;
+    c.deep = c.njobs < dm::kDeepWideCrossover;
+    if (!c.deep) {
+        // lanes of a warp run in lock step: keep neighbours the same length
+        std::vector<uint32_t> order(c.njobs);
+        for (uint32_t i = 0; i < c.njobs; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](uint32_t a, uint32_t b) { return c.h_jobs[a].nbytes > c.h_jobs[b].nbytes; });
+        std::vector<dm::HashJob> tmp(c.h_jobs, c.h_jobs + c.njobs);
+        std::vector<std::shared_ptr<Stream>> st2(c.njobs);
+        std::vector<uint8_t> fin2(c.njobs);
+        for (uint32_t i = 0; i < c.njobs; ++i) { c.h_jobs[i] = tmp[order[i]]; st2[i] = c.streams[order[i]]; fin2[i] = c.is_final[order[i]]; }
+        c.streams.swap(st2); c.is_final.swap(fin2);
     }
+    cudaMemcpyAsync(c.d_jobs, c.h_jobs, sizeof(dm::HashJob) * c.njobs, cudaMemcpyHostToDevice, e->hash_stream);
+    cudaEventRecord(c.k_start, e->hash_stream);
+    if (c.deep) { dm::launch_sha256_deep(c.d_jobs, c.njobs, e->d_states, e->d_digests, e->hash_stream, e->variant_deep); e->st_deep++; }
+    else { dm::launch_sha256_wide(c.d_jobs, c.njobs, e->d_states, e->d_digests, e->hash_stream, e->variant_wide); e->st_wide++; }
+    e->st_launches++;
     cudaEventRecord(c.k_end, e->hash_stream);
     c.busy = true;
     return true;
 }
 
+// The pump owns all launch decisions.  Policy: at most ONE hash launch in
+// flight.  While it runs, streams keep accumulating DMA'd bytes; the moment it
+// completes, the next launch takes everything that accumulated.  Launching
+// earlier would only fragment the same bytes over more, emptier launches (a
+// launch costs its longest lane no matter how many lanes it has).
 void pump_main(dm_engine *e)
 {
     cudaSetDevice(e->device);
-    int head = 0, tail = 0, inflight = 0;   // cycles[tail..head) busy
-    std::vector<std::shared_ptr<Stream>> work;
+    int cyc = 0;                    // next Cycle to use
+    Cycle *inflight = nullptr;
+    int b_head = 0, b_tail = 0, b_live = 0;
+    std::vector<std::shared_ptr<Stream>> ready, inbox;
     std::vector<Slab *> slabs;
     for (;;) {
-        // reap in order
-        while (inflight) {
-            Cycle &c = e->cycles[tail];
-            if (!c.slabs_released) {
-                bool done = true;
-                for (int i = 0; i < kCopyStreams; ++i) done = done && cudaEventQuery(c.copy_ev[i]) == cudaSuccess;
-                if (done) { for (Slab *s : c.slabs) slab_put(e, s); c.slabs.clear(); c.slabs_released = true; }
-            }
-            if (cudaEventQuery(c.k_end) != cudaSuccess) break;
-            reap_cycle(e, c);
-            tail = (tail + 1) % kCycles; --inflight;
+        // 1. ring slabs whose DMA has completed go back to the writers
+        while (b_live) {
+            SlabBatch &b = e->batches[b_tail];
+            bool done = true;
+            for (int i = 0; i < kCopyStreams; ++i) done = done && cudaEventQuery(b.ev[i]) == cudaSuccess;
+            if (!done) break;
+            for (Slab *sl : b.slabs) slab_put(e, sl);
+            b.slabs.clear(); b.busy = false;
+            b_tail = (b_tail + 1) % kSlabBatches; --b_live;
         }
+        // 2. finished hash launch
+        if (inflight && cudaEventQuery(inflight->k_end) == cudaSuccess) { reap_cycle(e, *inflight); inflight = nullptr; }
+        // 3. inbox
         bool stopping;
         {
             std::unique_lock<std::mutex> g(e->work_mu);
+            const bool idle = !inflight && !b_live && ready.empty() && slabs.empty();
             if (e->dirty.empty() && e->pending_slabs.empty() && !e->stop) {
-                if (inflight) e->work_cv.wait_for(g, std::chrono::microseconds(50));
-                else e->work_cv.wait(g, [&] { return !e->dirty.empty() || !e->pending_slabs.empty() || e->stop; });
+                if (idle) e->work_cv.wait(g, [&] { return !e->dirty.empty() || !e->pending_slabs.empty() || e->stop; });
+                else if (inflight || b_live) e->work_cv.wait_for(g, std::chrono::microseconds(40));
             }
             stopping = e->stop;
-            if (inflight < kCycles) { work.swap(e->dirty); slabs.swap(e->pending_slabs); }
+            inbox.swap(e->dirty);
+            if (slabs.empty()) slabs.swap(e->pending_slabs);
+            else { slabs.insert(slabs.end(), e->pending_slabs.begin(), e->pending_slabs.end()); e->pending_slabs.clear(); }
         }
-        if (!work.empty() || !slabs.empty()) {
-            if (run_cycle(e, e->cycles[head], work, slabs)) { head = (head + 1) % kCycles; ++inflight; }
-        } else if (inflight == kCycles) {
-            cudaEventSynchronize(e->cycles[tail].k_end);
+        for (auto &sp : inbox) ready.push_back(sp);
+        inbox.clear();
+        // 4. tag the newly DMA'd slabs with copy events
+        if (!slabs.empty() && b_live < kSlabBatches) {
+            SlabBatch &b = e->batches[b_head];
+            b.slabs.swap(slabs);
+            for (int i = 0; i < kCopyStreams; ++i) cudaEventRecord(b.ev[i], e->copy_stream[i]);
+            b.busy = true;
+            b_head = (b_head + 1) % kSlabBatches; ++b_live;
         }
-        if (stopping && inflight == 0) {
+        // 5. launch
+        if (!inflight && !ready.empty()) {
+            Cycle &c = e->cycles[cyc];
+            if (run_cycle(e, c, ready)) { inflight = &c; cyc = (cyc + 1) % kCycles; }
+        }
+        if (stopping && !inflight && !b_live && ready.empty() && slabs.empty()) {
             std::lock_guard<std::mutex> g(e->work_mu);
             if (e->dirty.empty() && e->pending_slabs.empty()) break;
         }
@@ -779,16 +803,23 @@ void spill_main(dm_engine *e)
 
 std::shared_ptr<Stream> find_stream(dm_engine *e, uint64_t id)
 {
-    std::lock_guard<std::mutex> g(e->mu);
-    auto it = e->streams.find(id);
-    return it == e->streams.end() ? nullptr : it->second;
+    const int k = (int)(id % kStripes);
+    std::lock_guard<std::mutex> g(e->stripe_mu[k]);
+    auto it = e->streams[k].find(id);
+    return it == e->streams[k].end() ? nullptr : it->second;
 }
 
 void drop_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, bool release_slot)
 {
-    std::lock_guard<std::mutex> g(e->mu);
-    e->streams.erase(sp->id);
-    if (release_slot) e->free_slots.push_back(sp->slot);
+    const int k = (int)(sp->id % kStripes);
+    {
+        std::lock_guard<std::mutex> g(e->stripe_mu[k]);
+        if (e->streams[k].erase(sp->id)) e->n_streams--;
+    }
+    if (release_slot) {
+        std::lock_guard<std::mutex> g(e->mu);
+        e->free_slots.push_back(sp->slot);
+    }
 }
 
 int ensure_ingest_scratch(dm_engine *e, uint32_t n)
@@ -873,6 +904,8 @@ void dm_engine_destroy(dm_engine *e)
         if (c.h_jobs) cudaFreeHost(c.h_jobs);
         if (c.d_jobs) cudaFree(c.d_jobs);
     }
+    for (SlabBatch &b : e->batches)
+        for (int i = 0; i < kCopyStreams; ++i) if (b.ev[i]) cudaEventDestroy(b.ev[i]);
     for (Bounce &b : e->bounce_store) { if (b.host) cudaFreeHost(b.host); if (b.stream) cudaStreamDestroy(b.stream); }
     if (e->ing_states) { cudaFree(e->ing_states); cudaFree(e->ing_digests); cudaFree(e->ing_jobs_d);
                          cudaFreeHost(e->ing_jobs_h); cudaFreeHost(e->ing_digests_h); }
@@ -908,6 +941,13 @@ int dm_engine_create(const dm_config *cfg, dm_engine **out)
     e->device = cfg->device;
     if (cfg->cas_dir) e->cas_dir = cfg->cas_dir;
     e->cfg.cas_dir = nullptr;
+    if (const char *v = getenv("DM_KERNEL_VARIANT")) {   // "wide,deep" variant numbers; experiments only
+        int w = -1, d = -1;
+        if (sscanf(v, "%d,%d", &w, &d) >= 1) {
+            if (w >= 0 && w < 15) e->variant_wide = w;
+            if (d >= 0 && d <= 2) e->variant_deep = d;
+        }
+    }
     if (!e->cfg.slab_bytes) e->cfg.slab_bytes = 1u << 20;
     if (!e->cfg.ring_bytes) e->cfg.ring_bytes = 256ull << 20;
     if (!e->cfg.max_streams) e->cfg.max_streams = 65536;
@@ -960,6 +1000,8 @@ int dm_engine_create(const dm_config *cfg, dm_engine **out)
         CU_INIT(cudaHostAlloc(&c.h_jobs, sizeof(dm::HashJob) * (uint64_t)e->max_jobs, cudaHostAllocDefault));
         CU_INIT(cudaMalloc(&c.d_jobs, sizeof(dm::HashJob) * (uint64_t)e->max_jobs));
     }
+    for (SlabBatch &b : e->batches)
+        for (int i = 0; i < kCopyStreams; ++i) CU_INIT(cudaEventCreateWithFlags(&b.ev[i], cudaEventDisableTiming));
     e->bounce_store.resize(kBounces);
     for (Bounce &b : e->bounce_store) {
         CU_INIT(cudaHostAlloc(&b.host, kBounceBytes, cudaHostAllocDefault));
@@ -984,7 +1026,7 @@ int dm_engine_stats(dm_engine *e, dm_stats *o)
     { std::lock_guard<std::mutex> g(e->stat_mu); o->kernel_ms = e->st_kernel_ms; }
     o->h2d_bytes = e->st_h2d; o->d2h_bytes = e->st_d2h;
     { std::lock_guard<std::mutex> g(e->arena_mu); o->hbm_cas_used = e->arena.used(); o->hbm_cas_capacity = e->arena.capacity(); }
-    { std::lock_guard<std::mutex> g(e->mu); o->open_streams = e->streams.size(); }
+    o->open_streams = e->n_streams;
     return DM_OK;
 }
 
@@ -1015,8 +1057,10 @@ int dm_stream_open(dm_engine *e, const uint8_t expect[32], uint64_t size_hint, u
         sp->capacity = x.len;
     }
     {
-        std::lock_guard<std::mutex> g(e->mu);
-        e->streams[sp->id] = sp;
+        const int k = (int)(sp->id % kStripes);
+        std::lock_guard<std::mutex> g(e->stripe_mu[k]);
+        e->streams[k][sp->id] = sp;
+        e->n_streams++;
     }
     *id = sp->id;
     return DM_OK;
@@ -1027,7 +1071,6 @@ int dm_stream_write(dm_engine *e, uint64_t id, const void *buf, size_t len)
     if (!e || (!buf && len)) return fail(DM_EINVAL, "null argument");
     auto sp = find_stream(e, id);
     if (!sp) return fail(DM_EINVAL, "unknown stream id");
-    cudaSetDevice(e->device);
     Stream *s = sp.get();
     std::unique_lock<std::mutex> g(s->mu);
     if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open for write");
@@ -1073,7 +1116,6 @@ int dm_stream_commit(dm_engine *e, uint64_t id, size_t len)
     if (!e) return fail(DM_EINVAL, "null argument");
     auto sp = find_stream(e, id);
     if (!sp) return fail(DM_EINVAL, "unknown stream id");
-    cudaSetDevice(e->device);
     Stream *s = sp.get();
     std::lock_guard<std::mutex> g(s->mu);
     if (!s->window_out) return fail(DM_ESTATE, "no window outstanding");
@@ -1318,7 +1360,7 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
         const uint64_t len = lengths[i];
         dm::HashJob &jb = e->ing_jobs_h[i];
         jb.src = base + offsets[i]; jb.dst = nullptr; jb.nbytes = len; jb.total_len = len;
-        jb.slot = i; jb.flags = dm::JOB_INIT | dm::JOB_FINAL; jb.pad_ = 0;
+        jb.slot = i; jb.flags = dm::JOB_INIT | dm::JOB_FINAL; jb.one = 1; jb.pad_ = 0;
         if (!hash_only) {
             Extent x;
             if (!arena_alloc(e, len, &x)) { cleanup(); return fail(DM_ENOMEM, "HBM CAS arena exhausted"); }
@@ -1342,8 +1384,8 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
     cudaError_t err = cudaMemcpyAsync(e->ing_jobs_d, e->ing_jobs_h, sizeof(dm::HashJob) * (uint64_t)n, cudaMemcpyHostToDevice, st);
     if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev0, st);
     if (err == cudaSuccess)
-        err = deep ? dm::launch_sha256_deep(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st)
-                   : dm::launch_sha256_wide(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st);
+        err = deep ? dm::launch_sha256_deep(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, e->variant_deep)
+                   : dm::launch_sha256_wide(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, e->variant_wide);
     if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev1, st);
     if (err == cudaSuccess) err = cudaMemcpyAsync(e->ing_digests_h, e->ing_digests, 32ull * n, cudaMemcpyDeviceToHost, st);
     if (err == cudaSuccess) err = cudaStreamSynchronize(st);

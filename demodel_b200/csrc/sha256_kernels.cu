@@ -72,34 +72,117 @@ __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 
     0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, \
     0xc67178f2u
 
+// Addition on the FMA pipe.  The integer ALU pipe (SHF/LOP3/IADD3) is the
+// bottleneck of SHA-256 on this part: ~84% of the round instructions can only
+// run there.  IMAD runs on the other (FMA) pipe, so `a*one + b` with a
+// *runtime* one (a kernel argument: ptxas cannot fold it back into IADD3)
+// moves the additions off the critical pipe.  kFma = 0 leaves the choice to
+// ptxas, 1 forces every round/schedule addition onto the FMA pipe with the
+// multiplier as a constant-bank operand, 2 does the same with the multiplier
+// held in a register (loaded from the job record).
+template <int kFma>
+__device__ __forceinline__ uint32_t addf(uint32_t a, uint32_t b, uint32_t one)
+{
+    if constexpr (kFma == 0) {
+        return a + b;
+    } else {
+        uint32_t d;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+        return d;
+    }
+}
+
 // One round, FIPS 180-4 §6.2.2 step 3, with the a..h rotation done by
 // renaming: v[] is indexed modulo 8 by the (compile-time) round number.
 //   T1 = h + S1(e) + Ch(e,f,g) + (K+W);  d += T1;  h = T1 + S0(a) + Maj(a,b,c)
-#define DM_ROUND(v, t, kw)                                                              \
-    do {                                                                                \
-        uint32_t t1_ = v[(7 - (t)) & 7] + big_sigma1(v[(4 - (t)) & 7]) +                \
-                       f_ch(v[(4 - (t)) & 7], v[(5 - (t)) & 7], v[(6 - (t)) & 7]) + (kw); \
-        uint32_t t2_ = big_sigma0(v[(0 - (t)) & 7]) +                                   \
-                       f_maj(v[(0 - (t)) & 7], v[(1 - (t)) & 7], v[(2 - (t)) & 7]);     \
-        v[(3 - (t)) & 7] += t1_;                                                        \
-        v[(7 - (t)) & 7] = t1_ + t2_;                                                   \
-    } while (0)
+template <int kFma, int t>
+__device__ __forceinline__ void sha_round(uint32_t (&v)[8], uint32_t kw, uint32_t one)
+{
+    constexpr int ia = (0 - t) & 7, ib = (1 - t) & 7, ic = (2 - t) & 7, id = (3 - t) & 7;
+    constexpr int ie = (4 - t) & 7, jf = (5 - t) & 7, ig = (6 - t) & 7, ih = (7 - t) & 7;
+    if constexpr (kFma == 0) {
+        const uint32_t t1 = v[ih] + big_sigma1(v[ie]) + f_ch(v[ie], v[jf], v[ig]) + kw;
+        const uint32_t t2 = big_sigma0(v[ia]) + f_maj(v[ia], v[ib], v[ic]);
+        v[id] += t1;
+        v[ih] = t1 + t2;
+    } else {
+        const uint32_t x = addf<1>(v[ih], kw, one);
+        const uint32_t y = addf<1>(x, f_ch(v[ie], v[jf], v[ig]), one);
+        const uint32_t t1 = addf<1>(y, big_sigma1(v[ie]), one);
+        const uint32_t t2 = addf<1>(big_sigma0(v[ia]), f_maj(v[ia], v[ib], v[ic]), one);
+        v[id] = addf<1>(v[id], t1, one);
+        v[ih] = addf<1>(t1, t2, one);
+    }
+}
+
+template <int kFma, int t0>
+__device__ __forceinline__ void sha_rounds4(uint32_t (&v)[8], const uint4 &k4, uint32_t one)
+{
+    sha_round<kFma, t0>(v, k4.x, one);
+    sha_round<kFma, t0 + 1>(v, k4.y, one);
+    sha_round<kFma, t0 + 2>(v, k4.z, one);
+    sha_round<kFma, t0 + 3>(v, k4.w, one);
+}
+
+template <int kFma, int t>
+struct RoundsFrom {   // compile-time unrolled t..63, W in registers, K as immediates
+    static __device__ __forceinline__ void run(uint32_t (&v)[8], uint32_t (&w)[16], uint32_t one)
+    {
+        constexpr uint32_t K[64] = {DM_K256_TABLE};
+        if constexpr (t >= 16) {
+            const uint32_t s = addf<kFma>(addf<kFma>(small_sigma1(w[(t - 2) & 15]), w[(t - 7) & 15], one),
+                                          small_sigma0(w[(t - 15) & 15]), one);
+            w[t & 15] = addf<kFma>(w[t & 15], s, one);
+        }
+        sha_round<kFma, t>(v, addf<kFma>(w[t & 15], K[t], one), one);
+        if constexpr (t < 63) RoundsFrom<kFma, t + 1>::run(v, w, one);
+    }
+};
 
 // Whole-block compression with everything in registers.  w[] holds the 16
 // big-endian message words and is clobbered (rolling 16-word schedule).
-__device__ __forceinline__ void compress_regs(uint32_t (&s)[8], uint32_t (&w)[16])
+template <int kFma>
+__device__ __forceinline__ void compress_regs(uint32_t (&s)[8], uint32_t (&w)[16], uint32_t one)
 {
-    constexpr uint32_t K[64] = {DM_K256_TABLE};
     uint32_t v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = s[i];
+    RoundsFrom<kFma, 0>::run(v, w, one);
 #pragma unroll
-    for (int t = 0; t < 16; ++t) DM_ROUND(v, t, K[t] + w[t]);
-#pragma unroll
-    for (int t = 16; t < 64; ++t) {
-        w[t & 15] += small_sigma1(w[(t - 2) & 15]) + w[(t - 7) & 15] + small_sigma0(w[(t - 15) & 15]);
-        DM_ROUND(v, t, K[t] + w[t & 15]);
+    for (int i = 0; i < 8; ++i) s[i] += v[i];
+}
+
+// Round constants for the rolled form below (uniform index -> constant-bank operand).
+__constant__ uint32_t c_K256[64] = {DM_K256_TABLE};
+
+template <int kFma, int j>
+struct Rounds16 {   // 16 rounds starting at a multiple of 16 (t0 >= 16: with message schedule)
+    template <bool kSched>
+    static __device__ __forceinline__ void run(uint32_t (&v)[8], uint32_t (&w)[16], int t0, uint32_t one)
+    {
+        if constexpr (kSched) {
+            const uint32_t s = addf<kFma>(addf<kFma>(small_sigma1(w[(j - 2) & 15]), w[(j - 7) & 15], one),
+                                          small_sigma0(w[(j - 15) & 15]), one);
+            w[j] = addf<kFma>(w[j], s, one);
+        }
+        sha_round<kFma, j>(v, addf<kFma>(w[j], c_K256[t0 + j], one), one);
+        if constexpr (j < 15) Rounds16<kFma, j + 1>::template run<kSched>(v, w, t0, one);
     }
+};
+
+// Same function as compress_regs with the rounds rolled 16 at a time: ~6 KB
+// of code instead of ~22 KB, so two of them plus the loads stay resident in
+// the instruction cache (ncu on the fully unrolled form: `no_instruction`
+// was the second-largest stall after the ALU pipe itself).
+template <int kFma>
+__device__ __forceinline__ void compress_rolled(uint32_t (&s)[8], uint32_t (&w)[16], uint32_t one)
+{
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = s[i];
+    Rounds16<kFma, 0>::template run<false>(v, w, 0, one);
+#pragma unroll 1
+    for (int t0 = 16; t0 < 64; t0 += 16) Rounds16<kFma, 0>::template run<true>(v, w, t0, one);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] += v[i];
 }
@@ -132,8 +215,10 @@ __device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v)
 // right after the message, zeros, and the 64-bit big-endian bit length in
 // the last two words of the last block.  Loads touch only 16-byte pieces
 // that hold at least one message byte.
+template <int kFma>
 __device__ __forceinline__ void hash_tail(uint32_t (&s)[8], const uint8_t *src, uint8_t *dst,
-                                          uint32_t rem, bool final, uint64_t total_len, bool do_store)
+                                          uint32_t rem, bool final, uint64_t total_len, bool do_store,
+                                          uint32_t one)
 {
     const uint32_t nvb = final ? ((rem + 72u) >> 6) : (rem >> 6);
     const uint64_t bits = total_len << 3;
@@ -161,7 +246,7 @@ __device__ __forceinline__ void hash_tail(uint32_t (&s)[8], const uint8_t *src, 
             }
             if (vb == nvb - 1) { w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
         }
-        compress_regs(s, w);
+        compress_rolled<kFma>(s, w, one);
     }
 }
 
@@ -200,8 +285,8 @@ __device__ __forceinline__ HashJob load_job(const HashJob *jobs, uint32_t j)
     jb.dst = reinterpret_cast<uint8_t *>(((uint64_t)a.w << 32) | a.z);
     jb.nbytes = ((uint64_t)b.y << 32) | b.x;
     jb.total_len = ((uint64_t)b.w << 32) | b.z;
-    const uint2 c = __ldg(reinterpret_cast<const uint2 *>(p + 2));
-    jb.slot = c.x; jb.flags = c.y; jb.pad_ = 0;
+    const uint4 c = __ldg(p + 2);
+    jb.slot = c.x; jb.flags = c.y; jb.one = c.z; jb.pad_ = 0;
     return jb;
 }
 
@@ -210,9 +295,16 @@ __device__ __forceinline__ HashJob load_job(const HashJob *jobs, uint32_t j)
 // ---------------------------------------------------------------------------
 constexpr int kWideThreads = 128;
 
-__global__ void __launch_bounds__(kWideThreads)
+// kStyle selects the shape of the main loop (all bit-identical):
+//   0  one 128-byte line (two blocks) per iteration, rounds fully unrolled  (~44 KB of code)
+//   1  one 64-byte block per iteration, rounds fully unrolled               (~22 KB)
+//   2  one 128-byte line per iteration, rounds rolled 16 at a time          (~20 KB)
+//   3  one 64-byte block per iteration, rolled                              (~10 KB)
+//   4  as 2, with the loads software-pipelined half a line ahead
+template <int kFma, int kStyle>
+__global__ void __launch_bounds__(kWideThreads, kStyle == 4 ? 5 : 1)
 sha256_wide_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *__restrict__ states,
-                   uint32_t *__restrict__ digests)
+                   uint32_t *__restrict__ digests, uint32_t one)
 {
     const uint32_t j = blockIdx.x * kWideThreads + threadIdx.x;
     if (j >= njobs) return;
@@ -220,29 +312,86 @@ sha256_wide_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
     uint32_t s[8];
     load_state(s, states, jb.slot, jb.flags);
 
+    if constexpr (kFma == 2) one = jb.one;          // register operand instead of c[0][..]
     const uint4 *p = reinterpret_cast<const uint4 *>(jb.src);
     uint4 *q = reinterpret_cast<uint4 *>(jb.dst);
     const bool copy = q != nullptr;
-    uint64_t npair = jb.nbytes >> 7;               // 128-byte lines
-#pragma unroll 1
-    for (; npair != 0; --npair) {
+    uint32_t rem;
+    if constexpr (kStyle == 4) {
+        // rolled rounds, loads software-pipelined half a line ahead: the second half of the
+        // current line and the first half of the next one are in flight during a compression
+        uint64_t npair = jb.nbytes >> 7;
         uint4 x[8];
+        if (npair) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = ld_stream(p + i);
-        if (copy) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) st_stream(q + i, x[i]);
-            q += 8;
+            for (int i = 0; i < 4; ++i) x[i] = ld_stream(p + i);
         }
-        p += 8;
-        uint32_t w[16];
-        unpack_be(w, x[0], x[1], x[2], x[3]);
-        compress_regs(s, w);
-        unpack_be(w, x[4], x[5], x[6], x[7]);
-        compress_regs(s, w);
+#pragma unroll 1
+        for (; npair != 0; --npair) {
+#pragma unroll
+            for (int i = 4; i < 8; ++i) x[i] = ld_stream(p + i);
+            if (copy) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) st_stream(q + i, x[i]);
+            }
+            uint32_t w[16];
+            unpack_be(w, x[0], x[1], x[2], x[3]);
+            p += 8;
+            if (npair > 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) x[i] = ld_stream(p + i);
+            }
+            compress_rolled<kFma>(s, w, one);
+            if (copy) {
+#pragma unroll
+                for (int i = 4; i < 8; ++i) st_stream(q + i, x[i]);
+                q += 8;
+            }
+            unpack_be(w, x[4], x[5], x[6], x[7]);
+            compress_rolled<kFma>(s, w, one);
+        }
+        rem = (uint32_t)(jb.nbytes & 127u);
+    } else if constexpr (kStyle == 0 || kStyle == 2) {
+        uint64_t npair = jb.nbytes >> 7;               // 128-byte lines
+#pragma unroll 1
+        for (; npair != 0; --npair) {
+            uint4 x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = ld_stream(p + i);
+            if (copy) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) st_stream(q + i, x[i]);
+                q += 8;
+            }
+            p += 8;
+            uint32_t w[16];
+            unpack_be(w, x[0], x[1], x[2], x[3]);
+            if constexpr (kStyle == 0) compress_regs<kFma>(s, w, one); else compress_rolled<kFma>(s, w, one);
+            unpack_be(w, x[4], x[5], x[6], x[7]);
+            if constexpr (kStyle == 0) compress_regs<kFma>(s, w, one); else compress_rolled<kFma>(s, w, one);
+        }
+        rem = (uint32_t)(jb.nbytes & 127u);
+    } else {
+        uint64_t nblk = jb.nbytes >> 6;
+#pragma unroll 1
+        for (; nblk != 0; --nblk) {
+            uint4 x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = ld_stream(p + i);
+            if (copy) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) st_stream(q + i, x[i]);
+                q += 4;
+            }
+            p += 4;
+            uint32_t w[16];
+            unpack_be(w, x[0], x[1], x[2], x[3]);
+            if constexpr (kStyle == 1) compress_regs<kFma>(s, w, one); else compress_rolled<kFma>(s, w, one);
+        }
+        rem = (uint32_t)(jb.nbytes & 63u);
     }
-    hash_tail(s, reinterpret_cast<const uint8_t *>(p), reinterpret_cast<uint8_t *>(q),
-              (uint32_t)(jb.nbytes & 127u), (jb.flags & JOB_FINAL) != 0, jb.total_len, true);
+    hash_tail<kFma>(s, reinterpret_cast<const uint8_t *>(p), reinterpret_cast<uint8_t *>(q), rem,
+                    (jb.flags & JOB_FINAL) != 0, jb.total_len, true, one);
     store_state(s, states, digests, jb.slot, jb.flags);
 }
 
@@ -253,9 +402,10 @@ constexpr int kDeepWarps = 1;                 // warps per CTA; 1 lets the block
                                               // spread few streams over all 592 sub-partitions
 constexpr int kKwStride = 68;                 // words per staged block: 64 + 4 pad -> conflict-free STS.128
 
+template <int kFma>
 __global__ void __launch_bounds__(32 * kDeepWarps)
 sha256_deep_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *__restrict__ states,
-                   uint32_t *__restrict__ digests)
+                   uint32_t *__restrict__ digests, uint32_t one)
 {
     __shared__ __align__(16) uint32_t kw_smem[kDeepWarps][32 * kKwStride];
     constexpr uint32_t K[64] = {DM_K256_TABLE};
@@ -267,6 +417,7 @@ sha256_deep_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
     uint32_t s[8];
     load_state(s, states, jb.slot, jb.flags);
     uint32_t *kw = kw_smem[wid];
+    if constexpr (kFma == 2) one = jb.one;
 
     const uint64_t nblk = jb.nbytes >> 6;
     const uint64_t ngroups = (nblk + 31) >> 5;
@@ -318,22 +469,22 @@ sha256_deep_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
             uint32_t v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = s[i];
-#pragma unroll
-            for (int t = 0; t < 64; t += 4) {
-                const uint4 k4 = kp[t >> 2];
-                DM_ROUND(v, t, k4.x);
-                DM_ROUND(v, t + 1, k4.y);
-                DM_ROUND(v, t + 2, k4.z);
-                DM_ROUND(v, t + 3, k4.w);
-            }
+            sha_rounds4<kFma, 0>(v, kp[0], one);   sha_rounds4<kFma, 4>(v, kp[1], one);
+            sha_rounds4<kFma, 8>(v, kp[2], one);   sha_rounds4<kFma, 12>(v, kp[3], one);
+            sha_rounds4<kFma, 16>(v, kp[4], one);  sha_rounds4<kFma, 20>(v, kp[5], one);
+            sha_rounds4<kFma, 24>(v, kp[6], one);  sha_rounds4<kFma, 28>(v, kp[7], one);
+            sha_rounds4<kFma, 32>(v, kp[8], one);  sha_rounds4<kFma, 36>(v, kp[9], one);
+            sha_rounds4<kFma, 40>(v, kp[10], one); sha_rounds4<kFma, 44>(v, kp[11], one);
+            sha_rounds4<kFma, 48>(v, kp[12], one); sha_rounds4<kFma, 52>(v, kp[13], one);
+            sha_rounds4<kFma, 56>(v, kp[14], one); sha_rounds4<kFma, 60>(v, kp[15], one);
 #pragma unroll
             for (int i = 0; i < 8; ++i) s[i] += v[i];
         }
         __syncwarp();
     }
     const uint64_t done = nblk << 6;
-    hash_tail(s, jb.src + done, copy ? jb.dst + done : nullptr, (uint32_t)(jb.nbytes & 63u),
-              (jb.flags & JOB_FINAL) != 0, jb.total_len, lane == 0);
+    hash_tail<kFma>(s, jb.src + done, copy ? jb.dst + done : nullptr, (uint32_t)(jb.nbytes & 63u),
+                    (jb.flags & JOB_FINAL) != 0, jb.total_len, lane == 0, one);
     if (lane == 0) store_state(s, states, digests, jb.slot, jb.flags);
 }
 
@@ -388,21 +539,39 @@ __global__ void synth_fill_many_kernel(uint64_t seed, uint64_t first_blob, uint8
 
 }  // namespace
 
+template <int kFma, int kStyle>
+static void launch_wide_t(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests, cudaStream_t stream)
+{
+    const uint32_t grid = (njobs + kWideThreads - 1) / kWideThreads;
+    sha256_wide_kernel<kFma, kStyle><<<grid, kWideThreads, 0, stream>>>(jobs, njobs, states, digests, 1u);
+}
+
+// variant = fma + 3 * style   (fma 0..2, style 0..4)
 cudaError_t launch_sha256_wide(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests,
-                               cudaStream_t stream)
+                               cudaStream_t stream, int variant)
 {
     if (njobs == 0) return cudaSuccess;
-    const uint32_t grid = (njobs + kWideThreads - 1) / kWideThreads;
-    sha256_wide_kernel<<<grid, kWideThreads, 0, stream>>>(jobs, njobs, states, digests);
+    switch (variant) {
+#define DM_W(f, st) case (f) + 3 * (st): launch_wide_t<f, st>(jobs, njobs, states, digests, stream); break;
+    DM_W(0, 0) DM_W(1, 0) DM_W(2, 0) DM_W(0, 1) DM_W(1, 1) DM_W(2, 1)
+    DM_W(0, 2) DM_W(1, 2) DM_W(2, 2) DM_W(0, 3) DM_W(1, 3) DM_W(2, 3)
+    DM_W(0, 4) DM_W(1, 4) DM_W(2, 4)
+#undef DM_W
+    default: launch_wide_t<kDefaultWideVariant % 3, kDefaultWideVariant / 3>(jobs, njobs, states, digests, stream); break;
+    }
     return cudaGetLastError();
 }
 
 cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests,
-                               cudaStream_t stream)
+                               cudaStream_t stream, int variant)
 {
     if (njobs == 0) return cudaSuccess;
     const uint32_t grid = (njobs + kDeepWarps - 1) / kDeepWarps;
-    sha256_deep_kernel<<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests);
+    switch (variant) {
+    case 0: sha256_deep_kernel<0><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, 1u); break;
+    case 2: sha256_deep_kernel<2><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, 1u); break;
+    default: sha256_deep_kernel<1><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, 1u); break;
+    }
     return cudaGetLastError();
 }
 

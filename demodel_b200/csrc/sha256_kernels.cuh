@@ -16,7 +16,8 @@ struct alignas(16) HashJob {
     uint64_t total_len;    // whole-blob length (used when FINAL)
     uint32_t slot;         // index into the state table
     uint32_t flags;        // JOB_*
-    uint64_t pad_;
+    uint32_t one;          // always 1: a multiplier the compiler cannot see (FMA-pipe adds)
+    uint32_t pad_;
 };
 static_assert(sizeof(HashJob) == 48, "HashJob layout is shared with the kernels");
 
@@ -27,10 +28,16 @@ enum : uint32_t {
 
 // states/digests: uint32[slot][8], native word order (host serialises big-endian).
 // `digests` may live in mapped pinned host memory.
+// variant (tuning knob, every value is bit-identical): for the wide kernel
+// fma + 3*style, for the deep kernel fma, where fma = how round additions are
+// issued (0 = ptxas' choice, 1 = all on the FMA pipe, 2 = FMA pipe with the
+// shortest e-chain) and style = main-loop shape (see sha256_wide_kernel).
 cudaError_t launch_sha256_wide(const HashJob *jobs, uint32_t njobs, uint32_t *states,
-                               uint32_t *digests, cudaStream_t stream);
+                               uint32_t *digests, cudaStream_t stream, int variant);
 cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *states,
-                               uint32_t *digests, cudaStream_t stream);
+                               uint32_t *digests, cudaStream_t stream, int variant);
+constexpr int kDefaultWideVariant = 7;
+constexpr int kDefaultDeepVariant = 0;
 
 // Live streams below this count go to the warp-per-stream (deep) kernel,
 // above it to the lane-per-stream (wide) kernel; see DESIGN.md §4.

@@ -182,7 +182,7 @@ class Engine:
     # -- device-resident ingest ---------------------------------------------------
     def ingest_device(self, dev_base: int, offsets: Sequence[int], lengths: Sequence[int],
                       expect: Optional[bytes] = None, hash_only: bool = False, replace: bool = False,
-                      kernel: Optional[str] = None) -> tuple[list[bytes], list[bool], float]:
+                      kernel: Optional[str] = None, raw: bool = False):
         """Hash-and-cache blobs already in HBM: blob i = [dev_base+offsets[i], +lengths[i]).
         Returns (digests, matched, kernel_ms)."""
         off = np.ascontiguousarray(np.asarray(offsets, dtype=np.uint64))
@@ -209,6 +209,8 @@ class Engine:
         check(self._lib.dm_ingest_device(self._h, C.c_void_p(dev_base), off.ctypes.data_as(u64p),
                                          ln.ctypes.data_as(u64p), n, exp, C.c_void_p(dig.ctypes.data),
                                          C.c_void_p(mat.ctypes.data), flags, C.byref(ms)), "dm_ingest_device")
+        if raw:                               # no per-blob Python objects (large n inside timed loops)
+            return dig[:32 * n], mat[:n], ms.value
         digs = [dig[32 * i:32 * i + 32].tobytes() for i in range(n)]
         return digs, [bool(x) for x in mat[:n]], ms.value
 
