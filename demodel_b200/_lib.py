@@ -53,6 +53,7 @@ class DmStats(C.Structure):
         ("hbm_cas_used", C.c_uint64),
         ("hbm_cas_capacity", C.c_uint64),
         ("open_streams", C.c_uint64),
+        ("ring_waits", C.c_uint64),
     ]
 
 
@@ -73,6 +74,7 @@ SIGNATURES = {
     "dm_stream_write": (C.c_int, [_P, C.c_uint64, _P, C.c_size_t]),
     "dm_stream_acquire": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "dm_stream_commit": (C.c_int, [_P, C.c_uint64, C.c_size_t]),
+    "dm_stream_flush": (C.c_int, [_P, C.c_uint64]),
     "dm_stream_finish": (C.c_int, [_P, C.c_uint64, _P, C.POINTER(C.c_int)]),
     "dm_stream_abort": (C.c_int, [_P, C.c_uint64]),
     "dm_cache_contains": (C.c_int, [_P, _P, _U64P]),

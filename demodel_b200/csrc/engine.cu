@@ -68,7 +68,7 @@ int fail_cuda(cudaError_t err, const char *where)
 
 constexpr uint64_t kAlign = 256;           // CAS extent granularity
 constexpr uint64_t kMaxGrow = 256ull << 20;
-constexpr int kCycles = 2;                 // hash launch descriptors (one in flight, one being built)
+constexpr int kCycles = 8;                 // concurrent hash launches, each on its own CUDA stream
 constexpr int kSlabBatches = 64;           // groups of DMA'd slabs waiting for their copy events
 constexpr int kStripes = 64;               // stream-table lock stripes
 constexpr int kCopyStreams = 2;
@@ -195,6 +195,7 @@ struct Cycle {
     bool busy = false;
     cudaEvent_t copy_ev[kCopyStreams]{};
     cudaEvent_t k_start{}, k_end{};
+    cudaStream_t stream{};           // launches on different streams overlap on the GPU
     dm::HashJob *h_jobs = nullptr;   // pinned
     dm::HashJob *d_jobs = nullptr;
     uint32_t njobs = 0;
@@ -222,7 +223,7 @@ struct dm_engine {
     int variant_wide = dm::kDefaultWideVariant, variant_deep = dm::kDefaultDeepVariant;   // DM_KERNEL_VARIANT overrides (tuning only)
 
     cudaStream_t copy_stream[kCopyStreams]{};
-    cudaStream_t hash_stream{}, ingest_stream{}, util_stream{};
+    cudaStream_t ingest_stream{}, util_stream{};
 
     uint8_t *arena_base = nullptr;
     std::mutex arena_mu;
@@ -279,7 +280,7 @@ struct dm_engine {
 
     // stats
     std::atomic<uint64_t> st_ingested{0}, st_hashed{0}, st_served{0}, st_committed{0}, st_mismatch{0};
-    std::atomic<uint64_t> st_launches{0}, st_wide{0}, st_deep{0}, st_h2d{0}, st_d2h{0};
+    std::atomic<uint64_t> st_launches{0}, st_wide{0}, st_deep{0}, st_h2d{0}, st_d2h{0}, st_ring_waits{0};
     std::mutex stat_mu;
     double st_kernel_ms = 0.0;
 };
@@ -390,6 +391,7 @@ int ensure_capacity(dm_engine *e, Stream *s, uint64_t need)
 Slab *slab_get(dm_engine *e)
 {
     std::unique_lock<std::mutex> g(e->slab_mu);
+    if (e->slab_free.empty() && !e->stop) e->st_ring_waits++;
     e->slab_cv.wait(g, [&] { return !e->slab_free.empty() || e->stop; });
     if (e->slab_free.empty()) return nullptr;
     Slab *s = e->slab_free.back();
@@ -585,18 +587,22 @@ void reap_cycle(dm_engine *e, Cycle &c)
     c.njobs = 0; c.bytes = 0; c.busy = false;
 }
 
-// Build one job per ready stream and launch ONE multi-buffer kernel over them.
-// Streams that still have unhashed bytes afterwards stay in `ready`.
+// Build one job per eligible ready stream and launch ONE multi-buffer kernel
+// over them on this cycle's CUDA stream.  Streams that still have unhashed
+// bytes afterwards (or a job in flight) stay in `ready`.
 bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &ready)
 {
     c.njobs = 0; c.bytes = 0;
-    const uint64_t quantum = (uint64_t)e->cfg.slab_bytes * 2;   // bounds one launch's longest lane
+    // One slab per job: a launch lasts as long as its longest lane, so lanes are kept the same
+    // length (streams holding more simply go again in the next launch, which overlaps this one).
+    const uint64_t quantum = (uint64_t)e->cfg.slab_bytes;
     std::vector<std::shared_ptr<Stream>> again;
     for (auto &sp : ready) {
         Stream *s = sp.get();
         std::lock_guard<std::mutex> g(s->mu);
         if (s->st == St::Aborted || s->st == St::Done || s->final_issued) { s->queued = false; continue; }
-        if (c.njobs >= e->max_jobs) { again.push_back(sp); continue; }
+        // one job per stream in flight: its next job chains on the state this one writes
+        if (s->jobs_inflight || c.njobs >= e->max_jobs) { again.push_back(sp); continue; }
         const bool finishing = s->st == St::Finishing;
         uint64_t n = finishing ? (s->received - s->hash_issued) : ((s->dma_issued - s->hash_issued) & ~63ull);
         if (!finishing && n == 0) { s->queued = false; continue; }
@@ -624,7 +630,7 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
     // Everything whose DMA was enqueued before this point is covered by these events.
     for (int i = 0; i < kCopyStreams; ++i) {
         cudaEventRecord(c.copy_ev[i], e->copy_stream[i]);
-        cudaStreamWaitEvent(e->hash_stream, c.copy_ev[i], 0);
+        cudaStreamWaitEvent(c.stream, c.copy_ev[i], 0);
     }
     c.deep = c.njobs < dm::kDeepWideCrossover;
     if (!c.deep) {
@@ -639,29 +645,32 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
         for (uint32_t i = 0; i < c.njobs; ++i) { c.h_jobs[i] = tmp[order[i]]; st2[i] = c.streams[order[i]]; fin2[i] = c.is_final[order[i]]; }
         c.streams.swap(st2); c.is_final.swap(fin2);
     }
-    cudaMemcpyAsync(c.d_jobs, c.h_jobs, sizeof(dm::HashJob) * c.njobs, cudaMemcpyHostToDevice, e->hash_stream);
-    cudaEventRecord(c.k_start, e->hash_stream);
-    if (c.deep) { dm::launch_sha256_deep(c.d_jobs, c.njobs, e->d_states, e->d_digests, e->hash_stream, e->variant_deep); e->st_deep++; }
-    else { dm::launch_sha256_wide(c.d_jobs, c.njobs, e->d_states, e->d_digests, e->hash_stream, e->variant_wide); e->st_wide++; }
+    cudaMemcpyAsync(c.d_jobs, c.h_jobs, sizeof(dm::HashJob) * c.njobs, cudaMemcpyHostToDevice, c.stream);
+    cudaEventRecord(c.k_start, c.stream);
+    if (c.deep) { dm::launch_sha256_deep(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_deep); e->st_deep++; }
+    else { dm::launch_sha256_wide(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_wide); e->st_wide++; }
     e->st_launches++;
-    cudaEventRecord(c.k_end, e->hash_stream);
+    cudaEventRecord(c.k_end, c.stream);
     c.busy = true;
     return true;
 }
 
-// The pump owns all launch decisions.  Policy: at most ONE hash launch in
-// flight.  While it runs, streams keep accumulating DMA'd bytes; the moment it
-// completes, the next launch takes everything that accumulated.  Launching
-// earlier would only fragment the same bytes over more, emptier launches (a
-// launch costs its longest lane no matter how many lanes it has).
+// The pump owns all launch decisions.  Policy: at most one JOB PER STREAM in
+// flight (its next job chains on the state the running one writes), but up to
+// kCycles LAUNCHES in flight, each on its own CUDA stream.  A launch costs its
+// longest lane however few lanes it has, so a launch that caught only a few
+// early streams must not hold the others back: they go out in the next launch
+// and overlap with it on the GPU (a deep launch occupies one sub-partition per
+// job).  When every launch slot is busy the ready set simply accumulates.
 void pump_main(dm_engine *e)
 {
     cudaSetDevice(e->device);
-    int cyc = 0;                    // next Cycle to use
-    Cycle *inflight = nullptr;
+    int n_inflight = 0;
     int b_head = 0, b_tail = 0, b_live = 0;
     std::vector<std::shared_ptr<Stream>> ready, inbox;
     std::vector<Slab *> slabs;
+    bool retry_ready = false;       // ready streams blocked only by their own in-flight job
+    bool launched = false;
     for (;;) {
         // 1. ring slabs whose DMA has completed go back to the writers
         while (b_live) {
@@ -673,22 +682,26 @@ void pump_main(dm_engine *e)
             b.slabs.clear(); b.busy = false;
             b_tail = (b_tail + 1) % kSlabBatches; --b_live;
         }
-        // 2. finished hash launch
-        if (inflight && cudaEventQuery(inflight->k_end) == cudaSuccess) { reap_cycle(e, *inflight); inflight = nullptr; }
-        // 3. inbox
+        // 2. finished hash launches (any order)
+        bool reaped = false;
+        for (Cycle &c : e->cycles)
+            if (c.busy && cudaEventQuery(c.k_end) == cudaSuccess) { reap_cycle(e, c); --n_inflight; reaped = true; }
+        // 3. inbox.  Sleep unless the previous pass launched something (more may be launchable).
         bool stopping;
         {
             std::unique_lock<std::mutex> g(e->work_mu);
-            const bool idle = !inflight && !b_live && ready.empty() && slabs.empty();
-            if (e->dirty.empty() && e->pending_slabs.empty() && !e->stop) {
+            const bool idle = !n_inflight && !b_live && ready.empty() && slabs.empty();
+            if (e->dirty.empty() && e->pending_slabs.empty() && !e->stop && !launched && !reaped) {
                 if (idle) e->work_cv.wait(g, [&] { return !e->dirty.empty() || !e->pending_slabs.empty() || e->stop; });
-                else if (inflight || b_live) e->work_cv.wait_for(g, std::chrono::microseconds(40));
+                else e->work_cv.wait_for(g, std::chrono::microseconds(40));
             }
             stopping = e->stop;
             inbox.swap(e->dirty);
             if (slabs.empty()) slabs.swap(e->pending_slabs);
             else { slabs.insert(slabs.end(), e->pending_slabs.begin(), e->pending_slabs.end()); e->pending_slabs.clear(); }
         }
+        launched = false;
+        const bool fresh = !inbox.empty();
         for (auto &sp : inbox) ready.push_back(sp);
         inbox.clear();
         // 4. tag the newly DMA'd slabs with copy events
@@ -699,12 +712,22 @@ void pump_main(dm_engine *e)
             b.busy = true;
             b_head = (b_head + 1) % kSlabBatches; ++b_live;
         }
-        // 5. launch
-        if (!inflight && !ready.empty()) {
-            Cycle &c = e->cycles[cyc];
-            if (run_cycle(e, c, ready)) { inflight = &c; cyc = (cyc + 1) % kCycles; }
+        // 5. launch on a free slot.  With launches already running, let the ready set
+        //    build up to a worthwhile size first (they will all fit in one launch anyway).
+        if (!ready.empty() && n_inflight < kCycles && (fresh || reaped || !retry_ready)) {
+            const uint64_t open_now = e->n_streams;
+            const bool worthwhile = n_inflight == 0 || ready.size() * 8 >= open_now || ready.size() >= 4096;
+            if (worthwhile) {
+                for (Cycle &c : e->cycles) {
+                    if (c.busy) continue;
+                    const size_t before = ready.size();
+                    if (run_cycle(e, c, ready)) { ++n_inflight; retry_ready = false; launched = true; }
+                    else retry_ready = !ready.empty() && ready.size() == before;   // all blocked on their own jobs
+                    break;
+                }
+            }
         }
-        if (stopping && !inflight && !b_live && ready.empty() && slabs.empty()) {
+        if (stopping && !n_inflight && !b_live && ready.empty() && slabs.empty()) {
             std::lock_guard<std::mutex> g(e->work_mu);
             if (e->dirty.empty() && e->pending_slabs.empty()) break;
         }
@@ -899,6 +922,7 @@ void dm_engine_destroy(dm_engine *e)
     for (auto &kv : e->readers) if (kv.second->fd >= 0) close(kv.second->fd);
     for (Cycle &c : e->cycles) {
         for (int i = 0; i < kCopyStreams; ++i) if (c.copy_ev[i]) cudaEventDestroy(c.copy_ev[i]);
+        if (c.stream) cudaStreamDestroy(c.stream);
         if (c.k_start) cudaEventDestroy(c.k_start);
         if (c.k_end) cudaEventDestroy(c.k_end);
         if (c.h_jobs) cudaFreeHost(c.h_jobs);
@@ -916,7 +940,6 @@ void dm_engine_destroy(dm_engine *e)
     if (e->ring) cudaFreeHost(e->ring);
     if (e->arena_base) cudaFree(e->arena_base);
     for (int i = 0; i < kCopyStreams; ++i) if (e->copy_stream[i]) cudaStreamDestroy(e->copy_stream[i]);
-    if (e->hash_stream) cudaStreamDestroy(e->hash_stream);
     if (e->ingest_stream) cudaStreamDestroy(e->ingest_stream);
     if (e->util_stream) cudaStreamDestroy(e->util_stream);
     delete e;
@@ -966,7 +989,6 @@ int dm_engine_create(const dm_config *cfg, dm_engine **out)
     if (prop.major < 10) { fail(DM_ENODEV, "kernels are built for sm_100a only"); dm_engine_destroy(e); return DM_ENODEV; }
 
     for (int i = 0; i < kCopyStreams; ++i) CU_INIT(cudaStreamCreateWithFlags(&e->copy_stream[i], cudaStreamNonBlocking));
-    CU_INIT(cudaStreamCreateWithFlags(&e->hash_stream, cudaStreamNonBlocking));
     CU_INIT(cudaStreamCreateWithFlags(&e->ingest_stream, cudaStreamNonBlocking));
     CU_INIT(cudaStreamCreateWithFlags(&e->util_stream, cudaStreamNonBlocking));
     CU_INIT(cudaEventCreate(&e->ing_ev0));
@@ -995,6 +1017,7 @@ int dm_engine_create(const dm_config *cfg, dm_engine **out)
     e->max_jobs = e->cfg.max_streams;
     for (Cycle &c : e->cycles) {
         for (int i = 0; i < kCopyStreams; ++i) CU_INIT(cudaEventCreateWithFlags(&c.copy_ev[i], cudaEventDisableTiming));
+        CU_INIT(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
         CU_INIT(cudaEventCreate(&c.k_start));
         CU_INIT(cudaEventCreate(&c.k_end));
         CU_INIT(cudaHostAlloc(&c.h_jobs, sizeof(dm::HashJob) * (uint64_t)e->max_jobs, cudaHostAllocDefault));
@@ -1027,6 +1050,7 @@ int dm_engine_stats(dm_engine *e, dm_stats *o)
     o->h2d_bytes = e->st_h2d; o->d2h_bytes = e->st_d2h;
     { std::lock_guard<std::mutex> g(e->arena_mu); o->hbm_cas_used = e->arena.used(); o->hbm_cas_capacity = e->arena.capacity(); }
     o->open_streams = e->n_streams;
+    o->ring_waits = e->st_ring_waits;
     return DM_OK;
 }
 
@@ -1127,21 +1151,39 @@ int dm_stream_commit(dm_engine *e, uint64_t id, size_t len)
     return DM_OK;
 }
 
+// Flush the partial slab and hand the stream to the pump for its final job.  Stream mutex held.
+static int begin_finish(dm_engine *e, const std::shared_ptr<Stream> &sp)
+{
+    Stream *s = sp.get();
+    if (s->st == St::Finishing || s->st == St::Done) return DM_OK;
+    if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open");
+    int rc = submit_slab(e, sp);
+    if (rc != DM_OK) return rc;
+    s->st = St::Finishing;
+    mark_dirty(e, sp, nullptr);
+    return DM_OK;
+}
+
+int dm_stream_flush(dm_engine *e, uint64_t id)
+{
+    if (!e) return fail(DM_EINVAL, "null argument");
+    auto sp = find_stream(e, id);
+    if (!sp) return fail(DM_EINVAL, "unknown stream id");
+    std::lock_guard<std::mutex> g(sp->mu);
+    return begin_finish(e, sp);
+}
+
 int dm_stream_finish(dm_engine *e, uint64_t id, uint8_t digest_out[32], int *matched)
 {
     if (!e) return fail(DM_EINVAL, "null argument");
     auto sp = find_stream(e, id);
     if (!sp) return fail(DM_EINVAL, "unknown stream id");
-    cudaSetDevice(e->device);
     Stream *s = sp.get();
     std::shared_ptr<Blob> blob;
     {
         std::unique_lock<std::mutex> g(s->mu);
-        if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open");
-        int rc = submit_slab(e, sp);
+        int rc = begin_finish(e, sp);
         if (rc != DM_OK) return rc;
-        s->st = St::Finishing;
-        mark_dirty(e, sp, nullptr);
         s->cv.wait(g, [&] { return s->st == St::Done; });
         if (digest_out) memcpy(digest_out, s->digest.b, 32);
         if (matched) *matched = s->matched;

@@ -3,13 +3,17 @@
 //
 // In the reference, net/http runs one goroutine per client connection
 // (/root/reference/cmd/demodel/start.go:210-215) and goproxy reads the
-// response body on that goroutine in 32 KiB pieces.  Here one OS thread plays
-// one such goroutine: it takes the next blob, wraps its "upstream body" (a
-// region of caller-owned host memory) in a BodyTee, and pumps Read() until
-// EOF, exactly the loop goproxy's copy would run.
+// response body on that goroutine in 32 KiB pieces.  Here `nthreads` OS
+// threads play `concurrency` such goroutines the way the Go scheduler runs
+// them on GOMAXPROCS threads: each thread round-robins one piece at a time
+// over its share of live connections (a BodyTee over an "upstream body" that
+// is a region of caller-owned host memory), starts the final hash at EOF
+// without blocking (dm_stream_flush) and collects verdicts afterwards.
 #include "proxy_hooks.hpp"
 
+#include <algorithm>
 #include <atomic>
+#include <memory>
 #include <chrono>
 #include <thread>
 #include <vector>
@@ -43,42 +47,65 @@ extern "C" int dm_proxy_drive(dm_engine *e, const void *host_base, const uint64_
     if (!e || !offsets || (!host_base && n)) return DM_EINVAL;
     if (chunk == 0) chunk = 32768;                    // io.Copy's buffer
     if (concurrency == 0) concurrency = 1;
-    uint32_t workers = concurrency;
-    if (nthreads > 0 && (uint32_t)nthreads < workers) workers = (uint32_t)nthreads;
-    if (workers > n) workers = n ? n : 1;
+    if (concurrency > n) concurrency = n ? n : 1;
+    // `nthreads` OS threads play `concurrency` goroutines, like GOMAXPROCS; 0 = one thread per connection
+    uint32_t workers = nthreads > 0 ? (uint32_t)nthreads : concurrency;
+    if (workers > concurrency) workers = concurrency;
     std::atomic<uint32_t> next{0};
     std::atomic<int> first_err{DM_OK};
     const uint8_t *base = static_cast<const uint8_t *>(host_base);
 
-    auto worker = [&]() {
+    struct Conn {
+        uint32_t blob;
+        MemUpstream up;
+        dm::BodyTee tee;
+        Conn(dm_engine *e, uint32_t i, const uint8_t *p, uint64_t len, const uint8_t *exp)
+            : blob(i), up(p, len), tee(e, &up, exp, len) {}
+    };
+
+    auto worker = [&](uint32_t share) {
         std::vector<uint8_t> buf(zero_copy ? 0 : chunk);       // goproxy's copy buffer
-        for (;;) {
+        std::vector<std::unique_ptr<Conn>> live, draining;
+        auto note_err = [&](int rc) { int exp = DM_OK; first_err.compare_exchange_strong(exp, rc); };
+        auto open_next = [&]() -> bool {
             const uint32_t i = next.fetch_add(1);
-            if (i >= n) break;
-            const uint64_t len = offsets[i + 1] - offsets[i];
-            MemUpstream up(base + offsets[i], len);
-            dm::BodyTee tee(e, &up, expect ? expect + 32ull * i : nullptr, len);
-            long got;
-            if (zero_copy) {
-                const void *view = nullptr;
-                while ((got = tee.ReadInPlace(&view, chunk)) > 0) {}
-            } else {
-                while ((got = tee.Read(buf.data(), chunk)) > 0) {}
+            if (i >= n) return false;
+            live.emplace_back(new Conn(e, i, base + offsets[i], offsets[i + 1] - offsets[i],
+                                       expect ? expect + 32ull * i : nullptr));
+            return true;
+        };
+        auto collect = [&](Conn &c) {
+            if (c.tee.Wait() != DM_OK) { note_err(c.tee.status()); return; }
+            if (digests_out) memcpy(digests_out + 32ull * c.blob, c.tee.digest(), 32);
+            if (matched_out) matched_out[c.blob] = c.tee.matched() ? 1 : 0;
+        };
+        bool more = true;
+        while (more && live.size() < share) more = open_next();
+        while (!live.empty()) {
+            for (size_t k = 0; k < live.size();) {             // one piece per connection per turn
+                Conn &c = *live[k];
+                const long got = c.tee.Pump(buf.data(), chunk, zero_copy != 0);
+                if (got > 0) { ++k; continue; }
+                if (got < 0) note_err((int)got); else draining.push_back(std::move(live[k]));
+                live[k] = std::move(live.back());
+                live.pop_back();
+                if (more) more = open_next();
             }
-            if (got < 0 || tee.status() != DM_OK) {
-                int exp = DM_OK;
-                first_err.compare_exchange_strong(exp, got < 0 ? (int)got : tee.status());
-                continue;
+            if (draining.size() >= 4 * (size_t)share) {        // bound the slots held by finished bodies
+                for (auto &c : draining) collect(*c);
+                draining.clear();
             }
-            if (digests_out) memcpy(digests_out + 32ull * i, tee.digest(), 32);
-            if (matched_out) matched_out[i] = tee.matched() ? 1 : 0;
         }
+        for (auto &c : draining) collect(*c);
     };
 
     const double t0 = now_s();
     std::vector<std::thread> th;
     th.reserve(workers);
-    for (uint32_t t = 0; t < workers; ++t) th.emplace_back(worker);
+    for (uint32_t t = 0; t < workers; ++t) {
+        const uint32_t share = concurrency / workers + (t < concurrency % workers ? 1 : 0);
+        th.emplace_back(worker, share ? share : 1);
+    }
     for (auto &t : th) t.join();
     if (seconds) *seconds = now_s() - t0;
     return first_err.load();

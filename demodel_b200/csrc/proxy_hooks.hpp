@@ -70,6 +70,39 @@ public:
         return got;
     }
 
+    // Multiplexing drivers: Pump() moves one piece like Read()/ReadInPlace() but at EOF only
+    // *starts* the final hash (dm_stream_flush); Wait() then collects the verdict.  A Go
+    // goroutine would simply block in Read(); an OS thread playing many goroutines must not.
+    long Pump(void *scratch, size_t n, bool in_place)
+    {
+        if (rc_ != DM_OK) return rc_;
+        if (eof_ || flushed_) return 0;
+        long got;
+        if (in_place) {
+            void *win = nullptr;
+            size_t cap = 0;
+            rc_ = dm_stream_acquire(e_, id_, &win, &cap);
+            if (rc_ != DM_OK) { Abort(); return rc_; }
+            got = up_->Read(win, cap < n ? cap : n);
+            int rc2 = dm_stream_commit(e_, id_, got > 0 ? (size_t)got : 0);
+            if (got >= 0 && rc2 != DM_OK) { rc_ = rc2; Abort(); return rc_; }
+        } else {
+            got = up_->Read(scratch, n);
+            if (got > 0) {
+                rc_ = dm_stream_write(e_, id_, scratch, (size_t)got);
+                if (rc_ != DM_OK) { Abort(); return rc_; }
+            }
+        }
+        if (got < 0) { Abort(); return got; }
+        if (got == 0) {
+            rc_ = dm_stream_flush(e_, id_);
+            if (rc_ != DM_OK) { Abort(); return rc_; }
+            flushed_ = true;
+        }
+        return got;
+    }
+    int Wait() { return eof_ ? rc_ : Finish(); }
+
     // io.Closer: before EOF this is an abort; after EOF a no-op.
     int Close()
     {
@@ -99,7 +132,7 @@ private:
     Upstream *up_;
     uint64_t id_ = 0;
     int rc_ = DM_OK;
-    bool open_ = false, eof_ = false;
+    bool open_ = false, eof_ = false, flushed_ = false;
     int matched_ = 0;
     uint8_t digest_[32] = {0};
 };

@@ -103,6 +103,9 @@ class Engine:
     def stream_commit(self, sid: int, n: int) -> None:
         check(self._lib.dm_stream_commit(self._h, sid, n), "dm_stream_commit")
 
+    def stream_flush(self, sid: int) -> None:
+        check(self._lib.dm_stream_flush(self._h, sid), "dm_stream_flush")
+
     def stream_finish(self, sid: int) -> tuple[bytes, bool]:
         out = (C.c_uint8 * 32)()
         matched = C.c_int()

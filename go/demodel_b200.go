@@ -1,0 +1,270 @@
+// Package b200 is the cgo binding of libdemodel_b200.so for demodel's proxy.
+//
+// NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Go toolchain
+// (SURVEY.md §8c), so this file is source only.  Its C++ twin, which IS
+// compiled and tested here, is demodel_b200/csrc/proxy_hooks.hpp; keep the
+// two in step.
+//
+// Wiring (see INTEGRATION.md for the diff against cmd/demodel/start.go):
+//
+//	OnResponse (start.go:201-204)  resp.Body = b200.NewBodyTee(pool, resp.Body, oid, resp.ContentLength)
+//	OnRequest  (start.go:197-200)  if r := pool.Hit(oid); r != nil { return req, hitResponse(req, r) }
+//	start()    (start.go:167)      pool, err := b200.Open(b200.Config{...}); defer pool.Close()
+package b200
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../include
+#cgo LDFLAGS: -L${SRCDIR}/../demodel_b200 -ldemodel_b200 -Wl,-rpath,${SRCDIR}/../demodel_b200
+#include <stdlib.h>
+#include "demodel_b200.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"io"
+	"unsafe"
+)
+
+// Error is a negative dm_err from the engine.
+type Error struct {
+	Code   int
+	Detail string
+}
+
+func (e *Error) Error() string {
+	return fmt.Sprintf("demodel_b200: %s (%d): %s", C.GoString(C.dm_strerror(C.int(e.Code))), e.Code, e.Detail)
+}
+
+func check(rc C.int) error {
+	if rc == C.DM_OK {
+		return nil
+	}
+	return &Error{Code: int(rc), Detail: C.GoString(C.dm_last_error())}
+}
+
+// Config mirrors dm_config for one GPU.
+type Config struct {
+	HBMCacheBytes uint64 // 0 = half of free HBM
+	RingBytes     uint64 // 0 = 256 MiB
+	SlabBytes     uint32 // 0 = 1 MiB
+	MaxStreams    uint32 // 0 = 65536
+	CacheDir      string // "" = HBM tier only
+	DiskSync      bool
+}
+
+// Pool owns one engine per GPU and routes blobs by digest prefix
+// (dm_shard_of): independent streams, no collective.
+type Pool struct {
+	engines []*C.dm_engine
+}
+
+// Open creates an engine on every visible GPU.  There is no CPU fallback:
+// without a CUDA device this returns DM_ENODEV and the proxy should run
+// without the cache path.
+func Open(cfg Config) (*Pool, error) {
+	n := int(C.dm_device_count())
+	if n <= 0 {
+		return nil, &Error{Code: int(C.DM_ENODEV), Detail: "no CUDA device"}
+	}
+	p := &Pool{}
+	for dev := 0; dev < n; dev++ {
+		var c C.dm_config
+		c.struct_size = C.uint32_t(unsafe.Sizeof(c))
+		c.device = C.int32_t(dev)
+		c.hbm_cas_bytes = C.uint64_t(cfg.HBMCacheBytes)
+		c.ring_bytes = C.uint64_t(cfg.RingBytes)
+		c.slab_bytes = C.uint32_t(cfg.SlabBytes)
+		c.max_streams = C.uint32_t(cfg.MaxStreams)
+		var dir *C.char
+		if cfg.CacheDir != "" {
+			dir = C.CString(fmt.Sprintf("%s/gpu%d", cfg.CacheDir, dev))
+			defer C.free(unsafe.Pointer(dir))
+		}
+		c.cas_dir = dir
+		if cfg.DiskSync {
+			c.flags |= C.DM_F_DISK_SYNC
+		}
+		var e *C.dm_engine
+		if err := check(C.dm_engine_create(&c, &e)); err != nil {
+			p.Close()
+			return nil, err
+		}
+		p.engines = append(p.engines, e)
+	}
+	return p, nil
+}
+
+func (p *Pool) Close() {
+	for _, e := range p.engines {
+		C.dm_engine_destroy(e)
+	}
+	p.engines = nil
+}
+
+// engineFor picks the GPU that owns a digest; blobs with no known digest
+// are homed by a hash of the URL computed by the caller.
+func (p *Pool) engineFor(digest *[32]byte) *C.dm_engine {
+	i := C.dm_shard_of((*C.uint8_t)(unsafe.Pointer(&digest[0])), C.uint32_t(len(p.engines)))
+	return p.engines[int(i)]
+}
+
+// BodyTee is the io.ReadCloser the OnResponse hook installs around
+// resp.Body: bytes flow to the client unchanged while the engine hashes them
+// and lands them in the cache.
+type BodyTee struct {
+	e       *C.dm_engine
+	up      io.ReadCloser
+	id      C.uint64_t
+	open    bool
+	eof     bool
+	Digest  [32]byte
+	Matched bool
+}
+
+// NewBodyTee opens a stream.  expect may be nil (digest unknown up front);
+// home is then required to pick the GPU (e.g. a hash of the request URL).
+func NewBodyTee(p *Pool, up io.ReadCloser, expect *[32]byte, home *[32]byte, contentLength int64) (*BodyTee, error) {
+	key := expect
+	if key == nil {
+		key = home
+	}
+	t := &BodyTee{e: p.engineFor(key), up: up}
+	var ex *C.uint8_t
+	if expect != nil {
+		ex = (*C.uint8_t)(unsafe.Pointer(&expect[0]))
+	}
+	hint := C.uint64_t(0)
+	if contentLength > 0 {
+		hint = C.uint64_t(contentLength)
+	}
+	if err := check(C.dm_stream_open(t.e, ex, hint, &t.id)); err != nil {
+		return nil, err
+	}
+	t.open = true
+	return t, nil
+}
+
+// Read implements io.Reader for goproxy's copy loop.  dm_stream_write copies
+// p before returning, so goproxy may reuse its buffer.
+func (t *BodyTee) Read(p []byte) (int, error) {
+	if t.eof {
+		return 0, io.EOF
+	}
+	n, err := t.up.Read(p)
+	if n > 0 {
+		if werr := check(C.dm_stream_write(t.e, t.id, unsafe.Pointer(&p[0]), C.size_t(n))); werr != nil {
+			t.abort()
+			return n, werr
+		}
+	}
+	if errors.Is(err, io.EOF) {
+		return n, t.finish()
+	}
+	if err != nil {
+		t.abort()
+	}
+	return n, err
+}
+
+// WriteTo is the zero-copy path (io.Copy prefers io.WriterTo): each upstream
+// Read lands directly in a window of the engine's pinned ring.
+func (t *BodyTee) WriteTo(w io.Writer) (int64, error) {
+	var total int64
+	for {
+		var win unsafe.Pointer
+		var capN C.size_t
+		if err := check(C.dm_stream_acquire(t.e, t.id, &win, &capN)); err != nil {
+			t.abort()
+			return total, err
+		}
+		buf := unsafe.Slice((*byte)(win), int(capN))
+		n, rerr := t.up.Read(buf)
+		if err := check(C.dm_stream_commit(t.e, t.id, C.size_t(n))); err != nil {
+			t.abort()
+			return total, err
+		}
+		if n > 0 {
+			m, werr := w.Write(buf[:n]) // ring slab is stable until the next acquire
+			total += int64(m)
+			if werr != nil {
+				t.abort()
+				return total, werr
+			}
+		}
+		if errors.Is(rerr, io.EOF) {
+			if ferr := t.finish(); ferr != io.EOF {
+				return total, ferr
+			}
+			return total, nil
+		}
+		if rerr != nil {
+			t.abort()
+			return total, rerr
+		}
+	}
+}
+
+func (t *BodyTee) finish() error {
+	t.eof = true
+	t.open = false
+	var m C.int
+	if err := check(C.dm_stream_finish(t.e, t.id, (*C.uint8_t)(unsafe.Pointer(&t.Digest[0])), &m)); err != nil {
+		return err
+	}
+	t.Matched = m != 0
+	return io.EOF
+}
+
+func (t *BodyTee) abort() {
+	if t.open {
+		C.dm_stream_abort(t.e, t.id)
+		t.open = false
+	}
+}
+
+// Close before EOF means the client went away or upstream failed.
+func (t *BodyTee) Close() error {
+	t.abort()
+	return t.up.Close()
+}
+
+// HitReader is the body of the response the OnRequest hook synthesises on
+// a cache hit.
+type HitReader struct {
+	e    *C.dm_engine
+	id   C.uint64_t
+	Size int64
+	off  uint64
+}
+
+// Hit returns nil on a miss.
+func (p *Pool) Hit(digest *[32]byte) *HitReader {
+	e := p.engineFor(digest)
+	var id, size C.uint64_t
+	rc := C.dm_cache_open(e, (*C.uint8_t)(unsafe.Pointer(&digest[0])), &id, &size)
+	if rc != C.DM_OK {
+		return nil
+	}
+	return &HitReader{e: e, id: id, Size: int64(size)}
+}
+
+func (r *HitReader) Read(p []byte) (int, error) {
+	if len(p) == 0 {
+		return 0, nil
+	}
+	var n C.size_t
+	if err := check(C.dm_cache_read(r.e, r.id, C.uint64_t(r.off), unsafe.Pointer(&p[0]), C.size_t(len(p)), &n)); err != nil {
+		return 0, err
+	}
+	if n == 0 {
+		return 0, io.EOF
+	}
+	r.off += uint64(n)
+	return int(n), nil
+}
+
+func (r *HitReader) Close() error {
+	return check(C.dm_cache_close(r.e, r.id))
+}

@@ -84,6 +84,7 @@ typedef struct dm_stats {
     uint64_t hbm_cas_used;
     uint64_t hbm_cas_capacity;
     uint64_t open_streams;
+    uint64_t ring_waits;          /* times a writer had to wait for a free ring slab (back-pressure) */
 } dm_stats;
 
 /* ---- engine lifetime (start.go:167-216) -------------------------------- */
@@ -112,6 +113,10 @@ int dm_stream_write(dm_engine *e, uint64_t id, const void *buf, size_t len);
  * stream; *cap >= 1 on success. */
 int dm_stream_acquire(dm_engine *e, uint64_t id, void **ptr, size_t *cap);
 int dm_stream_commit(dm_engine *e, uint64_t id, size_t len);
+/* Optional, non-blocking: upstream hit EOF, no more bytes will be written.
+ * Starts the final hash so a later dm_stream_finish returns at once; lets one
+ * OS thread multiplex many connections (goroutines on GOMAXPROCS threads). */
+int dm_stream_flush(dm_engine *e, uint64_t id);
 /* Blocks until every byte is hashed.  digest_out receives the SHA-256 of
  * the bytes written.  *matched = 1 if expect was NULL or equals the digest
  * (the blob is then published in the CAS under digest_out), 0 otherwise (the
