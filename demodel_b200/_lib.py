@@ -57,6 +57,10 @@ class DmStats(C.Structure):
     ]
 
 
+class DmCheckpoint(C.Structure):
+    _fields_ = [("h", C.c_uint32 * 8), ("bytes", C.c_uint64), ("abi", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 # name -> (restype, argtypes); every symbol include/demodel_b200.h declares.
 _P = C.c_void_p
 _U8P = C.POINTER(C.c_uint8)
@@ -72,6 +76,9 @@ SIGNATURES = {
     "dm_shard_of": (C.c_uint32, [_P, C.c_uint32]),
     "dm_stream_open": (C.c_int, [_P, _P, C.c_uint64, _U64P]),
     "dm_stream_write": (C.c_int, [_P, C.c_uint64, _P, C.c_size_t]),
+    "dm_stream_write_at": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, C.c_size_t]),
+    "dm_stream_checkpoint": (C.c_int, [_P, C.c_uint64, C.POINTER(DmCheckpoint)]),
+    "dm_stream_resume": (C.c_int, [_P, C.POINTER(DmCheckpoint), _P, C.c_uint64, _U64P]),
     "dm_stream_acquire": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "dm_stream_commit": (C.c_int, [_P, C.c_uint64, C.c_size_t]),
     "dm_stream_flush": (C.c_int, [_P, C.c_uint64]),

@@ -169,11 +169,19 @@ struct Stream {
     Digest expect{};
     std::vector<Extent> extents;
     uint64_t capacity = 0;     // sum of extents
-    uint64_t received = 0;     // bytes accepted
-    uint64_t dma_issued = 0;   // bytes whose H2D is enqueued (== received - cur_fill)
+    uint64_t received = 0;     // bytes accepted (count, any order)
+    uint64_t dma_issued = 0;   // end of the contiguous run, starting at resume_base, whose H2D is enqueued
     uint64_t hash_issued = 0;  // bytes covered by launched jobs
-    Slab *cur = nullptr;
+    Slab *cur = nullptr;       // sequential cursor: stages [dma_issued, dma_issued + cur_fill)
     uint32_t cur_fill = 0;
+    // Range parts (dm_stream_write_at): out-of-order pieces staged per part, DMA'd to their place in
+    // the extent, and remembered as islands until the contiguous frontier reaches them.
+    struct Part { uint64_t base; Slab *slab; uint32_t fill; };
+    std::vector<Part> parts;
+    std::map<uint64_t, uint64_t> islands;        // [start, end) DMA-enqueued beyond the frontier
+    uint64_t resume_base = 0;                    // bytes hashed before this stream existed (checkpoint)
+    std::map<uint64_t, uint64_t> prefix_cover;   // what of [0, resume_base) was re-supplied for caching
+    bool ckpt_waiter = false;
     bool window_out = false;   // acquire() window outstanding
     bool queued = false;       // in the pump's inbox / ready list (guarded by mu)
     bool final_issued = false;
@@ -437,7 +445,47 @@ void mark_dirty(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *submitted
     e->work_cv.notify_one();
 }
 
-// DMA the stream's current slab to its place in the blob.  Stream mutex held.
+// DMA `n` staged bytes to blob offset `base`.  Stream mutex held.  The slab is handed to the pump
+// (released once its copy event completes) on success, returned to the ring on failure.
+int dma_range(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *slab, uint64_t base, uint32_t n)
+{
+    Stream *s = sp.get();
+    cudaSetDevice(e->device);       // the caller may be any OS thread (cgo)
+    int rc = ensure_capacity(e, s, base + n);
+    if (rc != DM_OK) { slab_put(e, slab); return rc; }
+    cudaStream_t cs = e->copy_stream[s->id % kCopyStreams];
+    const uint8_t *src = slab->host;
+    cudaError_t err = cudaSuccess;
+    for_segments(e, s->extents, base, n, [&](uint8_t *dev, uint64_t len) {
+        if (err == cudaSuccess) err = cudaMemcpyAsync(dev, src, len, cudaMemcpyHostToDevice, cs);
+        src += len;
+    });
+    if (err != cudaSuccess) { slab_put(e, slab); return fail_cuda(err, "cudaMemcpyAsync(H2D slab)"); }
+    e->st_h2d += n;
+    return DM_OK;
+}
+
+void add_interval(std::map<uint64_t, uint64_t> &m, uint64_t lo, uint64_t hi)
+{
+    if (lo >= hi) return;
+    auto it = m.lower_bound(lo);
+    if (it != m.begin()) { auto pv = std::prev(it); if (pv->second >= lo) { lo = pv->first; hi = std::max(hi, pv->second); it = m.erase(pv); } }
+    while (it != m.end() && it->first <= hi) { hi = std::max(hi, it->second); it = m.erase(it); }
+    m[lo] = hi;
+}
+
+// The contiguous frontier swallows islands that now touch it.  Stream mutex held.
+void absorb_islands(Stream *s)
+{
+    if (s->cur_fill) return;            // staged sequential bytes sit between the frontier and any island
+    auto it = s->islands.begin();
+    while (it != s->islands.end() && it->first <= s->dma_issued) {
+        s->dma_issued = std::max(s->dma_issued, it->second);
+        it = s->islands.erase(it);
+    }
+}
+
+// DMA the stream's sequential slab to its place in the blob.  Stream mutex held.
 int submit_slab(dm_engine *e, const std::shared_ptr<Stream> &sp)
 {
     Stream *s = sp.get();
@@ -446,21 +494,45 @@ int submit_slab(dm_engine *e, const std::shared_ptr<Stream> &sp)
     const uint32_t n = s->cur_fill;
     s->cur = nullptr; s->cur_fill = 0;
     if (n == 0) { slab_put(e, slab); return DM_OK; }
-    cudaSetDevice(e->device);       // the caller may be any OS thread (cgo)
-    int rc = ensure_capacity(e, s, s->dma_issued + n);
-    if (rc != DM_OK) { slab_put(e, slab); return rc; }
-    cudaStream_t cs = e->copy_stream[s->id % kCopyStreams];
-    const uint8_t *src = slab->host;
-    cudaError_t err = cudaSuccess;
-    for_segments(e, s->extents, s->dma_issued, n, [&](uint8_t *dev, uint64_t len) {
-        if (err == cudaSuccess) err = cudaMemcpyAsync(dev, src, len, cudaMemcpyHostToDevice, cs);
-        src += len;
-    });
-    if (err != cudaSuccess) { slab_put(e, slab); return fail_cuda(err, "cudaMemcpyAsync(H2D slab)"); }
+    int rc = dma_range(e, sp, slab, s->dma_issued, n);
+    if (rc != DM_OK) return rc;
     s->dma_issued += n;
-    e->st_h2d += n;
+    absorb_islands(s);
     mark_dirty(e, sp, slab);
     return DM_OK;
+}
+
+// DMA one range part.  Stream mutex held; invalidates indices into s->parts.
+int submit_part(dm_engine *e, const std::shared_ptr<Stream> &sp, size_t idx)
+{
+    Stream *s = sp.get();
+    Stream::Part pt = s->parts[idx];
+    s->parts.erase(s->parts.begin() + (long)idx);
+    if (pt.fill == 0) { slab_put(e, pt.slab); return DM_OK; }
+    int rc = dma_range(e, sp, pt.slab, pt.base, pt.fill);
+    if (rc != DM_OK) return rc;
+    if (pt.base + pt.fill <= s->resume_base) add_interval(s->prefix_cover, pt.base, pt.base + pt.fill);
+    else add_interval(s->islands, pt.base, pt.base + pt.fill);
+    absorb_islands(s);
+    mark_dirty(e, sp, pt.slab);
+    return DM_OK;
+}
+
+// Would [off, off+len) collide with bytes this stream already holds?  Stream mutex held.
+bool range_taken(const Stream *s, uint64_t off, uint64_t len, const Stream::Part *self)
+{
+    const uint64_t end = off + len;
+    auto hits = [&](uint64_t lo, uint64_t hi) { return lo < end && off < hi; };
+    if (hits(s->resume_base, s->dma_issued + s->cur_fill) && !(self == nullptr && off == s->dma_issued + s->cur_fill)) return true;
+    auto in_map = [&](const std::map<uint64_t, uint64_t> &m) {
+        auto it = m.upper_bound(off);
+        if (it != m.begin() && std::prev(it)->second > off) return true;
+        return it != m.end() && it->first < end;
+    };
+    if (in_map(s->islands) || in_map(s->prefix_cover)) return true;
+    for (const Stream::Part &p : s->parts)
+        if (&p != self && hits(p.base, p.base + p.fill)) return true;
+    return false;
 }
 
 // ---- CAS commit --------------------------------------------------------------
@@ -544,13 +616,17 @@ void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint
     std::vector<Extent> ext;
     ext.swap(s->extents);
     s->capacity = 0;
-    const uint64_t size = s->received;
+    const uint64_t size = s->dma_issued;
     const Digest d = s->digest;
     const int matched = s->matched;
+    // a resumed stream is cacheable only if the already-hashed prefix was re-supplied
+    const bool whole = s->resume_base == 0 ||
+                       (s->prefix_cover.size() == 1 && s->prefix_cover.begin()->first == 0 &&
+                        s->prefix_cover.begin()->second >= s->resume_base);
     g.unlock();
     std::shared_ptr<Blob> b;
-    if (matched) b = publish(e, d, size, ext);
-    else { free_extents(e, ext); e->st_mismatch++; }
+    if (matched && whole) b = publish(e, d, size, ext);
+    else { free_extents(e, ext); if (!matched) e->st_mismatch++; }
     g.lock();
     s->blob = b;
     s->st = St::Done;
@@ -569,12 +645,14 @@ void reap_cycle(dm_engine *e, Cycle &c)
     e->st_hashed += c.bytes;
     for (size_t i = 0; i < c.streams.size(); ++i) {
         std::shared_ptr<Stream> &sp = c.streams[i];
-        bool free_now = false;
+        bool free_now = false, wake = false;
         {
             std::lock_guard<std::mutex> g(sp->mu);
             sp->jobs_inflight--;
             free_now = sp->st == St::Aborted && sp->jobs_inflight == 0;
+            wake = sp->ckpt_waiter;
         }
+        if (wake) sp->cv.notify_all();
         if (free_now) {
             free_extents(e, sp->extents);
             std::lock_guard<std::mutex> g(e->mu);
@@ -604,7 +682,7 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
         // one job per stream in flight: its next job chains on the state this one writes
         if (s->jobs_inflight || c.njobs >= e->max_jobs) { again.push_back(sp); continue; }
         const bool finishing = s->st == St::Finishing;
-        uint64_t n = finishing ? (s->received - s->hash_issued) : ((s->dma_issued - s->hash_issued) & ~63ull);
+        uint64_t n = finishing ? (s->dma_issued - s->hash_issued) : ((s->dma_issued - s->hash_issued) & ~63ull);
         if (!finishing && n == 0) { s->queued = false; continue; }
         uint64_t contig = 0;
         uint8_t *src = n ? seg_at(e, s->extents, s->hash_issued, &contig) : nullptr;
@@ -612,7 +690,7 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
         if (n > contig && n) { n = contig; final = false; }          // stop at the extent boundary
         if (n > quantum) { n = quantum; final = false; }
         dm::HashJob &jb = c.h_jobs[c.njobs++];
-        jb.src = src; jb.dst = nullptr; jb.nbytes = n; jb.total_len = s->received; jb.slot = s->slot;
+        jb.src = src; jb.dst = nullptr; jb.nbytes = n; jb.total_len = s->dma_issued; jb.slot = s->slot;
         jb.flags = (s->hash_issued == 0 ? dm::JOB_INIT : 0u) | (final ? dm::JOB_FINAL : 0u);
         jb.one = 1; jb.pad_ = 0;
         s->hash_issued += n;
@@ -1106,6 +1184,8 @@ int dm_stream_write(dm_engine *e, uint64_t id, const void *buf, size_t len)
             if (rc != DM_OK) return rc;
         }
         const size_t n = std::min<size_t>(len, slab_bytes - s->cur_fill);
+        if ((!s->islands.empty() || !s->parts.empty()) && range_taken(s, s->dma_issued + s->cur_fill, n, nullptr))
+            return fail(DM_EINVAL, "write overlaps a range already received");
         memcpy(s->cur->host + s->cur_fill, p, n);
         s->cur_fill += (uint32_t)n; s->received += n; p += n; len -= n;
         e->st_ingested += n;
@@ -1113,6 +1193,111 @@ int dm_stream_write(dm_engine *e, uint64_t id, const void *buf, size_t len)
             int rc = submit_slab(e, sp);
             if (rc != DM_OK) return rc;
         }
+    }
+    return DM_OK;
+}
+
+int dm_stream_write_at(dm_engine *e, uint64_t id, uint64_t offset, const void *buf, size_t len)
+{
+    if (!e || (!buf && len)) return fail(DM_EINVAL, "null argument");
+    auto sp = find_stream(e, id);
+    if (!sp) return fail(DM_EINVAL, "unknown stream id");
+    Stream *s = sp.get();
+    std::unique_lock<std::mutex> g(s->mu);
+    if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open for write");
+    if (offset == s->dma_issued + s->cur_fill && s->parts.empty() && s->islands.empty()) {
+        g.unlock();
+        return dm_stream_write(e, id, buf, len);          // plain sequential continuation
+    }
+    const uint8_t *p = static_cast<const uint8_t *>(buf);
+    const uint32_t slab_bytes = e->cfg.slab_bytes;
+    while (len) {
+        // the part that ends exactly here, or a new one
+        size_t idx = s->parts.size();
+        for (size_t i = 0; i < s->parts.size(); ++i)
+            if (s->parts[i].base + s->parts[i].fill == offset) { idx = i; break; }
+        if (idx == s->parts.size()) {
+            if (offset == s->dma_issued + s->cur_fill) {
+                // continues the contiguous run: use the sequential cursor
+                if (!s->cur) {
+                    int rc = take_slab(e, s, g);
+                    if (rc != DM_OK) return rc;
+                    continue;                               // state may have moved while unlocked
+                }
+                const size_t n = std::min<size_t>(len, slab_bytes - s->cur_fill);
+                if (range_taken(s, offset, n, nullptr)) return fail(DM_EINVAL, "write overlaps a range already received");
+                memcpy(s->cur->host + s->cur_fill, p, n);
+                s->cur_fill += (uint32_t)n; s->received += n; p += n; len -= n; offset += n;
+                e->st_ingested += n;
+                if (s->cur_fill == slab_bytes) { int rc = submit_slab(e, sp); if (rc != DM_OK) return rc; }
+                continue;
+            }
+            if (s->parts.size() >= 64) return fail(DM_ENOMEM, "too many concurrent range parts on one stream");
+            if (range_taken(s, offset, 1, nullptr)) return fail(DM_EINVAL, "write overlaps a range already received");
+            g.unlock();
+            Slab *fresh = slab_get(e);
+            g.lock();
+            if (!fresh) return fail(DM_ESTATE, "engine stopping");
+            if (s->st != St::Open) { slab_put(e, fresh); return fail(DM_ESTATE, "stream closed while waiting for the ring"); }
+            s->parts.push_back({offset, fresh, 0});
+            continue;                                       // re-find (the vector may have changed while unlocked)
+        }
+        Stream::Part &pt = s->parts[idx];
+        const size_t n = std::min<size_t>(len, slab_bytes - pt.fill);
+        if (range_taken(s, offset, n, &pt)) return fail(DM_EINVAL, "write overlaps a range already received");
+        memcpy(pt.slab->host + pt.fill, p, n);
+        pt.fill += (uint32_t)n; s->received += n; p += n; len -= n; offset += n;
+        e->st_ingested += n;
+        if (pt.fill == slab_bytes) { int rc = submit_part(e, sp, idx); if (rc != DM_OK) return rc; }
+    }
+    return DM_OK;
+}
+
+int dm_stream_checkpoint(dm_engine *e, uint64_t id, dm_checkpoint *out)
+{
+    if (!e || !out) return fail(DM_EINVAL, "null argument");
+    auto sp = find_stream(e, id);
+    if (!sp) return fail(DM_EINVAL, "unknown stream id");
+    Stream *s = sp.get();
+    std::unique_lock<std::mutex> g(s->mu);
+    if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open");
+    {   // push out what is staged so the checkpoint covers every whole block received in order
+        int rc = submit_slab(e, sp);
+        if (rc != DM_OK) return rc;
+    }
+    // everything DMA'd so far in whole blocks must be hashed and no job may be running
+    s->ckpt_waiter = true;
+    s->cv.wait(g, [&] { return s->st != St::Open || (s->jobs_inflight == 0 && ((s->dma_issued - s->hash_issued) & ~63ull) == 0); });
+    s->ckpt_waiter = false;
+    if (s->st != St::Open) return fail(DM_ESTATE, "stream closed during checkpoint");
+    memset(out, 0, sizeof *out);
+    out->abi = DM_ABI_VERSION;
+    out->bytes = s->hash_issued;
+    if (s->hash_issued == 0) {
+        static const uint32_t iv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au,
+                                       0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+        memcpy(out->h, iv, sizeof iv);
+        return DM_OK;
+    }
+    cudaSetDevice(e->device);
+    CU_TRY(cudaMemcpy(out->h, e->d_states + 8ull * s->slot, 32, cudaMemcpyDeviceToHost));
+    return DM_OK;
+}
+
+int dm_stream_resume(dm_engine *e, const dm_checkpoint *ck, const uint8_t expect[32], uint64_t size_hint, uint64_t *id)
+{
+    if (!e || !ck || !id) return fail(DM_EINVAL, "null argument");
+    if (ck->abi != DM_ABI_VERSION || (ck->bytes & 63)) return fail(DM_EINVAL, "bad checkpoint");
+    int rc = dm_stream_open(e, expect, size_hint, id);
+    if (rc != DM_OK) return rc;
+    auto sp = find_stream(e, *id);
+    Stream *s = sp.get();
+    std::lock_guard<std::mutex> g(s->mu);
+    s->resume_base = s->dma_issued = s->hash_issued = ck->bytes;
+    if (ck->bytes) {
+        cudaSetDevice(e->device);
+        cudaError_t err = cudaMemcpy(e->d_states + 8ull * s->slot, ck->h, 32, cudaMemcpyHostToDevice);
+        if (err != cudaSuccess) { s->st = St::Aborted; return fail_cuda(err, "cudaMemcpy(checkpoint state)"); }
     }
     return DM_OK;
 }
@@ -1159,6 +1344,11 @@ static int begin_finish(dm_engine *e, const std::shared_ptr<Stream> &sp)
     if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open");
     int rc = submit_slab(e, sp);
     if (rc != DM_OK) return rc;
+    while (!s->parts.empty()) {
+        rc = submit_part(e, sp, s->parts.size() - 1);
+        if (rc != DM_OK) return rc;
+    }
+    if (!s->islands.empty()) return fail(DM_ESTATE, "blob has holes: ranges missing before the last byte");
     s->st = St::Finishing;
     mark_dirty(e, sp, nullptr);
     return DM_OK;
@@ -1210,6 +1400,8 @@ int dm_stream_abort(dm_engine *e, uint64_t id)
         std::lock_guard<std::mutex> g(s->mu);
         if (s->st == St::Done || s->st == St::Aborted) return fail(DM_ESTATE, "stream already closed");
         if (s->cur) { slab_put(e, s->cur); s->cur = nullptr; s->cur_fill = 0; }
+        for (Stream::Part &pt : s->parts) slab_put(e, pt.slab);
+        s->parts.clear();
         s->st = St::Aborted;
         free_now = s->jobs_inflight == 0;
     }

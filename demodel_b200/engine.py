@@ -95,6 +95,24 @@ class Engine:
         ptr, n = _buf_ptr(data)
         check(self._lib.dm_stream_write(self._h, sid, ptr, n), "dm_stream_write")
 
+    def stream_write_at(self, sid: int, offset: int, data) -> None:
+        """One piece of a Range part: bytes for blob offset `offset`, any order."""
+        ptr, n = _buf_ptr(data)
+        check(self._lib.dm_stream_write_at(self._h, sid, offset, ptr, n), "dm_stream_write_at")
+
+    def stream_checkpoint(self, sid: int) -> tuple[bytes, int]:
+        """(32-byte chaining value as 8 native words, bytes hashed) of an open stream."""
+        ck = _lib.DmCheckpoint()
+        check(self._lib.dm_stream_checkpoint(self._h, sid, C.byref(ck)), "dm_stream_checkpoint")
+        return bytes(ck), ck.bytes
+
+    def stream_resume(self, checkpoint: bytes, expect: Optional[bytes] = None, size_hint: int = 0) -> int:
+        ck = _lib.DmCheckpoint.from_buffer_copy(checkpoint)
+        sid = C.c_uint64()
+        check(self._lib.dm_stream_resume(self._h, C.byref(ck), _digest_arg(expect), size_hint, C.byref(sid)),
+              "dm_stream_resume")
+        return sid.value
+
     def stream_acquire(self, sid: int) -> tuple[int, int]:
         ptr, cap = C.c_void_p(), C.c_size_t()
         check(self._lib.dm_stream_acquire(self._h, sid, C.byref(ptr), C.byref(cap)), "dm_stream_acquire")

@@ -108,6 +108,28 @@ int dm_stream_open(dm_engine *e, const uint8_t expect[32], uint64_t size_hint, u
 /* Copies buf before returning (the Go caller reuses its 32 KiB io.Copy
  * buffer on the next Read).  Blocks only for ring back-pressure. */
 int dm_stream_write(dm_engine *e, uint64_t id, const void *buf, size_t len);
+/* Range parts: bytes for blob offset `offset`, in any order (HF clients and
+ * Ollama fetch one large blob as parallel `Range` requests).  The bytes land
+ * at their place in the blob's HBM extent at once; the digest advances over the
+ * contiguous prefix as it grows.  Ranges must not overlap; up to 64 parts may
+ * be open on one stream.  dm_stream_finish fails with DM_ESTATE while holes remain. */
+int dm_stream_write_at(dm_engine *e, uint64_t id, uint64_t offset, const void *buf, size_t len);
+
+/* Mid-state checkpoint / resume of an interrupted download.
+ * dm_stream_checkpoint waits until every whole block received in order is
+ * hashed and returns (state words, byte count).  dm_stream_resume opens a new
+ * stream that continues from such a checkpoint: bytes from `ck->bytes` on are
+ * hashed; the prefix may be re-supplied with dm_stream_write_at purely for
+ * caching — if it is not, the blob is verified but not published in the CAS. */
+typedef struct dm_checkpoint {
+    uint32_t h[8];      /* SHA-256 chaining value after `bytes` bytes */
+    uint64_t bytes;     /* multiple of 64 */
+    uint32_t abi;
+    uint32_t reserved;
+} dm_checkpoint;
+int dm_stream_checkpoint(dm_engine *e, uint64_t id, dm_checkpoint *out);
+int dm_stream_resume(dm_engine *e, const dm_checkpoint *ck, const uint8_t expect[32], uint64_t size_hint, uint64_t *id);
+
 /* Zero-copy variant: borrow a window of the pinned ring, Read() into it,
  * then commit the bytes actually read.  At most one outstanding window per
  * stream; *cap >= 1 on success. */
