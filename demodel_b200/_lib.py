@@ -54,7 +54,12 @@ class DmStats(C.Structure):
         ("hbm_cas_capacity", C.c_uint64),
         ("open_streams", C.c_uint64),
         ("ring_waits", C.c_uint64),
+        ("launches_group", C.c_uint64),
     ]
+
+
+class DmLayer(C.Structure):
+    _fields_ = [("digest", C.c_uint8 * 32), ("size", C.c_uint64), ("media_type", C.c_char * 96)]
 
 
 class DmCheckpoint(C.Structure):
@@ -91,6 +96,8 @@ SIGNATURES = {
     "dm_cache_evict": (C.c_int, [_P, _P]),
     "dm_cache_device_extents": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), _U64P, C.c_uint32]),
     "dm_ingest_device": (C.c_int, [_P, _P, _U64P, _U64P, C.c_uint32, _P, _P, _P, C.c_uint32, C.POINTER(C.c_double)]),
+    "dm_manifest_parse": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(DmLayer), C.c_uint32, C.POINTER(C.c_uint32)]),
+    "dm_manifest_prefetch": (C.c_int, [_P, C.POINTER(DmLayer), C.c_uint32, _U64P]),
     "dm_synth_fill_host": (None, [C.c_uint64, C.c_uint64, C.c_uint64, _P, C.c_size_t]),
     "dm_synth_fill_device": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P, C.c_size_t]),
     "dm_synth_fill_device_many": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, _U64P, _U64P, C.c_uint32]),

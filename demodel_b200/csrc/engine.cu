@@ -228,6 +228,7 @@ struct dm_engine {
     std::string cas_dir;
     int device = 0;
     int sm_count = 148;
+    int force_spw = 0;               // DM_FORCE_SPW: 1/2/4/8/16/32 streams per warp for every launch (tuning only)
     int variant_wide = dm::kDefaultWideVariant, variant_deep = dm::kDefaultDeepVariant;   // DM_KERNEL_VARIANT overrides (tuning only)
 
     cudaStream_t copy_stream[kCopyStreams]{};
@@ -288,6 +289,7 @@ struct dm_engine {
 
     // stats
     std::atomic<uint64_t> st_ingested{0}, st_hashed{0}, st_served{0}, st_committed{0}, st_mismatch{0};
+    std::atomic<uint64_t> st_group{0};
     std::atomic<uint64_t> st_launches{0}, st_wide{0}, st_deep{0}, st_h2d{0}, st_d2h{0}, st_ring_waits{0};
     std::mutex stat_mu;
     double st_kernel_ms = 0.0;
@@ -710,8 +712,9 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
         cudaEventRecord(c.copy_ev[i], e->copy_stream[i]);
         cudaStreamWaitEvent(c.stream, c.copy_ev[i], 0);
     }
-    c.deep = c.njobs < dm::kDeepWideCrossover;
-    if (!c.deep) {
+    const int spw = e->force_spw ? e->force_spw : dm::streams_per_warp_for(c.njobs);
+    c.deep = spw == 1;
+    if (spw > 1) {
         // lanes of a warp run in lock step: keep neighbours the same length
         std::vector<uint32_t> order(c.njobs);
         for (uint32_t i = 0; i < c.njobs; ++i) order[i] = i;
@@ -725,8 +728,9 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
     }
     cudaMemcpyAsync(c.d_jobs, c.h_jobs, sizeof(dm::HashJob) * c.njobs, cudaMemcpyHostToDevice, c.stream);
     cudaEventRecord(c.k_start, c.stream);
-    if (c.deep) { dm::launch_sha256_deep(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_deep); e->st_deep++; }
-    else { dm::launch_sha256_wide(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_wide); e->st_wide++; }
+    if (spw == 1) { dm::launch_sha256_deep(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_deep); e->st_deep++; }
+    else if (spw == 32) { dm::launch_sha256_wide(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_wide); e->st_wide++; }
+    else { dm::launch_sha256_group(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, spw); e->st_group++; }
     e->st_launches++;
     cudaEventRecord(c.k_end, c.stream);
     c.busy = true;
@@ -1042,11 +1046,15 @@ int dm_engine_create(const dm_config *cfg, dm_engine **out)
     e->device = cfg->device;
     if (cfg->cas_dir) e->cas_dir = cfg->cas_dir;
     e->cfg.cas_dir = nullptr;
+    if (const char *v = getenv("DM_FORCE_SPW")) {
+        const int f = atoi(v);
+        if (f == 1 || f == 2 || f == 4 || f == 8 || f == 16 || f == 32) e->force_spw = f;
+    }
     if (const char *v = getenv("DM_KERNEL_VARIANT")) {   // "wide,deep" variant numbers; experiments only
         int w = -1, d = -1;
         if (sscanf(v, "%d,%d", &w, &d) >= 1) {
-            if (w >= 0 && w < 15) e->variant_wide = w;
-            if (d >= 0 && d <= 2) e->variant_deep = d;
+            if (w >= 0 && w < 20) e->variant_wide = w;
+            if (d >= 0 && d <= 3) e->variant_deep = d;
         }
     }
     if (!e->cfg.slab_bytes) e->cfg.slab_bytes = 1u << 20;
@@ -1129,6 +1137,7 @@ int dm_engine_stats(dm_engine *e, dm_stats *o)
     { std::lock_guard<std::mutex> g(e->arena_mu); o->hbm_cas_used = e->arena.used(); o->hbm_cas_capacity = e->arena.capacity(); }
     o->open_streams = e->n_streams;
     o->ring_waits = e->st_ring_waits;
+    o->launches_group = e->st_group;
     return DM_OK;
 }
 
@@ -1603,12 +1612,14 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
         }
         total += len;
     }
-    bool deep = n < dm::kDeepWideCrossover;
-    if (flags & DM_ING_FORCE_WIDE) deep = false;
-    if (flags & DM_ING_FORCE_DEEP) deep = true;
+    int spw = e->force_spw ? e->force_spw : dm::streams_per_warp_for(n);
+    if (flags & DM_ING_FORCE_WIDE) spw = 32;
+    if (flags & DM_ING_FORCE_DEEP) spw = 1;
+    if (flags & DM_ING_SPW_MASK) spw = 1 << (((flags & DM_ING_SPW_MASK) >> DM_ING_SPW_SHIFT) - 1);
+    const bool deep = spw == 1;
     std::vector<uint32_t> order(n);
     for (uint32_t i = 0; i < n; ++i) order[i] = i;
-    if (!deep) {
+    if (spw > 1) {
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
             return e->ing_jobs_h[a].nbytes > e->ing_jobs_h[b].nbytes; });
         std::vector<dm::HashJob> tmp(e->ing_jobs_h, e->ing_jobs_h + n);
@@ -1618,8 +1629,9 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
     cudaError_t err = cudaMemcpyAsync(e->ing_jobs_d, e->ing_jobs_h, sizeof(dm::HashJob) * (uint64_t)n, cudaMemcpyHostToDevice, st);
     if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev0, st);
     if (err == cudaSuccess)
-        err = deep ? dm::launch_sha256_deep(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, e->variant_deep)
-                   : dm::launch_sha256_wide(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, e->variant_wide);
+        err = spw == 1 ? dm::launch_sha256_deep(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, e->variant_deep)
+            : spw == 32 ? dm::launch_sha256_wide(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, e->variant_wide)
+                        : dm::launch_sha256_group(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, spw);
     if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev1, st);
     if (err == cudaSuccess) err = cudaMemcpyAsync(e->ing_digests_h, e->ing_digests, 32ull * n, cudaMemcpyDeviceToHost, st);
     if (err == cudaSuccess) err = cudaStreamSynchronize(st);
@@ -1628,7 +1640,7 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
     cudaEventElapsedTime(&ms, e->ing_ev0, e->ing_ev1);
     if (kernel_ms) *kernel_ms = ms;
     { std::lock_guard<std::mutex> g(e->stat_mu); e->st_kernel_ms += ms; }
-    e->st_launches++; (deep ? e->st_deep : e->st_wide)++;
+    e->st_launches++; (spw == 1 ? e->st_deep : spw == 32 ? e->st_wide : e->st_group)++;
     e->st_hashed += total;
     for (uint32_t i = 0; i < n; ++i) {
         Digest d;

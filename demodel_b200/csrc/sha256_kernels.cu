@@ -72,6 +72,12 @@ __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 
     0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, \
     0xc67178f2u
 
+// Runtime constants for FMA-pipe tricks (kernel argument; values fixed by the launcher).
+struct FmaK {
+    uint32_t one;                         // 1
+    uint32_t pad[3];
+};
+
 // Addition on the FMA pipe.  The integer ALU pipe (SHF/LOP3/IADD3) is the
 // bottleneck of SHA-256 on this part: ~84% of the round instructions can only
 // run there.  IMAD runs on the other (FMA) pipe, so `a*one + b` with a
@@ -81,13 +87,13 @@ __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 
 // multiplier as a constant-bank operand, 2 does the same with the multiplier
 // held in a register (loaded from the job record).
 template <int kFma>
-__device__ __forceinline__ uint32_t addf(uint32_t a, uint32_t b, uint32_t one)
+__device__ __forceinline__ uint32_t addf(uint32_t a, uint32_t b, const FmaK &k)
 {
     if constexpr (kFma == 0) {
         return a + b;
     } else {
         uint32_t d;
-        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(k.one), "r"(b));
         return d;
     }
 }
@@ -96,7 +102,7 @@ __device__ __forceinline__ uint32_t addf(uint32_t a, uint32_t b, uint32_t one)
 // renaming: v[] is indexed modulo 8 by the (compile-time) round number.
 //   T1 = h + S1(e) + Ch(e,f,g) + (K+W);  d += T1;  h = T1 + S0(a) + Maj(a,b,c)
 template <int kFma, int t>
-__device__ __forceinline__ void sha_round(uint32_t (&v)[8], uint32_t kw, uint32_t one)
+__device__ __forceinline__ void sha_round(uint32_t (&v)[8], uint32_t kw, const FmaK &k)
 {
     constexpr int ia = (0 - t) & 7, ib = (1 - t) & 7, ic = (2 - t) & 7, id = (3 - t) & 7;
     constexpr int ie = (4 - t) & 7, jf = (5 - t) & 7, ig = (6 - t) & 7, ih = (7 - t) & 7;
@@ -106,48 +112,48 @@ __device__ __forceinline__ void sha_round(uint32_t (&v)[8], uint32_t kw, uint32_
         v[id] += t1;
         v[ih] = t1 + t2;
     } else {
-        const uint32_t x = addf<1>(v[ih], kw, one);
-        const uint32_t y = addf<1>(x, f_ch(v[ie], v[jf], v[ig]), one);
-        const uint32_t t1 = addf<1>(y, big_sigma1(v[ie]), one);
-        const uint32_t t2 = addf<1>(big_sigma0(v[ia]), f_maj(v[ia], v[ib], v[ic]), one);
-        v[id] = addf<1>(v[id], t1, one);
-        v[ih] = addf<1>(t1, t2, one);
+        const uint32_t x = addf<1>(v[ih], kw, k);
+        const uint32_t y = addf<1>(x, f_ch(v[ie], v[jf], v[ig]), k);
+        const uint32_t t1 = addf<1>(y, big_sigma1(v[ie]), k);
+        const uint32_t t2 = addf<1>(big_sigma0(v[ia]), f_maj(v[ia], v[ib], v[ic]), k);
+        v[id] = addf<1>(v[id], t1, k);
+        v[ih] = addf<1>(t1, t2, k);
     }
 }
 
 template <int kFma, int t0>
-__device__ __forceinline__ void sha_rounds4(uint32_t (&v)[8], const uint4 &k4, uint32_t one)
+__device__ __forceinline__ void sha_rounds4(uint32_t (&v)[8], const uint4 &k4, const FmaK &k)
 {
-    sha_round<kFma, t0>(v, k4.x, one);
-    sha_round<kFma, t0 + 1>(v, k4.y, one);
-    sha_round<kFma, t0 + 2>(v, k4.z, one);
-    sha_round<kFma, t0 + 3>(v, k4.w, one);
+    sha_round<kFma, t0>(v, k4.x, k);
+    sha_round<kFma, t0 + 1>(v, k4.y, k);
+    sha_round<kFma, t0 + 2>(v, k4.z, k);
+    sha_round<kFma, t0 + 3>(v, k4.w, k);
 }
 
 template <int kFma, int t>
 struct RoundsFrom {   // compile-time unrolled t..63, W in registers, K as immediates
-    static __device__ __forceinline__ void run(uint32_t (&v)[8], uint32_t (&w)[16], uint32_t one)
+    static __device__ __forceinline__ void run(uint32_t (&v)[8], uint32_t (&w)[16], const FmaK &k)
     {
         constexpr uint32_t K[64] = {DM_K256_TABLE};
         if constexpr (t >= 16) {
-            const uint32_t s = addf<kFma>(addf<kFma>(small_sigma1(w[(t - 2) & 15]), w[(t - 7) & 15], one),
-                                          small_sigma0(w[(t - 15) & 15]), one);
-            w[t & 15] = addf<kFma>(w[t & 15], s, one);
+            const uint32_t s = addf<kFma>(addf<kFma>(small_sigma1(w[(t - 2) & 15]), w[(t - 7) & 15], k),
+                                          small_sigma0(w[(t - 15) & 15]), k);
+            w[t & 15] = addf<kFma>(w[t & 15], s, k);
         }
-        sha_round<kFma, t>(v, addf<kFma>(w[t & 15], K[t], one), one);
-        if constexpr (t < 63) RoundsFrom<kFma, t + 1>::run(v, w, one);
+        sha_round<kFma, t>(v, addf<kFma>(w[t & 15], K[t], k), k);
+        if constexpr (t < 63) RoundsFrom<kFma, t + 1>::run(v, w, k);
     }
 };
 
 // Whole-block compression with everything in registers.  w[] holds the 16
 // big-endian message words and is clobbered (rolling 16-word schedule).
 template <int kFma>
-__device__ __forceinline__ void compress_regs(uint32_t (&s)[8], uint32_t (&w)[16], uint32_t one)
+__device__ __forceinline__ void compress_regs(uint32_t (&s)[8], uint32_t (&w)[16], const FmaK &k)
 {
     uint32_t v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = s[i];
-    RoundsFrom<kFma, 0>::run(v, w, one);
+    RoundsFrom<kFma, 0>::run(v, w, k);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] += v[i];
 }
@@ -158,15 +164,15 @@ __constant__ uint32_t c_K256[64] = {DM_K256_TABLE};
 template <int kFma, int j>
 struct Rounds16 {   // 16 rounds starting at a multiple of 16 (t0 >= 16: with message schedule)
     template <bool kSched>
-    static __device__ __forceinline__ void run(uint32_t (&v)[8], uint32_t (&w)[16], int t0, uint32_t one)
+    static __device__ __forceinline__ void run(uint32_t (&v)[8], uint32_t (&w)[16], int t0, const FmaK &k)
     {
         if constexpr (kSched) {
-            const uint32_t s = addf<kFma>(addf<kFma>(small_sigma1(w[(j - 2) & 15]), w[(j - 7) & 15], one),
-                                          small_sigma0(w[(j - 15) & 15]), one);
-            w[j] = addf<kFma>(w[j], s, one);
+            const uint32_t s = addf<kFma>(addf<kFma>(small_sigma1(w[(j - 2) & 15]), w[(j - 7) & 15], k),
+                                          small_sigma0(w[(j - 15) & 15]), k);
+            w[j] = addf<kFma>(w[j], s, k);
         }
-        sha_round<kFma, j>(v, addf<kFma>(w[j], c_K256[t0 + j], one), one);
-        if constexpr (j < 15) Rounds16<kFma, j + 1>::template run<kSched>(v, w, t0, one);
+        sha_round<kFma, j>(v, addf<kFma>(w[j], c_K256[t0 + j], k), k);
+        if constexpr (j < 15) Rounds16<kFma, j + 1>::template run<kSched>(v, w, t0, k);
     }
 };
 
@@ -175,14 +181,14 @@ struct Rounds16 {   // 16 rounds starting at a multiple of 16 (t0 >= 16: with me
 // the instruction cache (ncu on the fully unrolled form: `no_instruction`
 // was the second-largest stall after the ALU pipe itself).
 template <int kFma>
-__device__ __forceinline__ void compress_rolled(uint32_t (&s)[8], uint32_t (&w)[16], uint32_t one)
+__device__ __forceinline__ void compress_rolled(uint32_t (&s)[8], uint32_t (&w)[16], const FmaK &k)
 {
     uint32_t v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = s[i];
-    Rounds16<kFma, 0>::template run<false>(v, w, 0, one);
+    Rounds16<kFma, 0>::template run<false>(v, w, 0, k);
 #pragma unroll 1
-    for (int t0 = 16; t0 < 64; t0 += 16) Rounds16<kFma, 0>::template run<true>(v, w, t0, one);
+    for (int t0 = 16; t0 < 64; t0 += 16) Rounds16<kFma, 0>::template run<true>(v, w, t0, k);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] += v[i];
 }
@@ -218,7 +224,7 @@ __device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v)
 template <int kFma>
 __device__ __forceinline__ void hash_tail(uint32_t (&s)[8], const uint8_t *src, uint8_t *dst,
                                           uint32_t rem, bool final, uint64_t total_len, bool do_store,
-                                          uint32_t one)
+                                          const FmaK &k)
 {
     const uint32_t nvb = final ? ((rem + 72u) >> 6) : (rem >> 6);
     const uint64_t bits = total_len << 3;
@@ -246,7 +252,7 @@ __device__ __forceinline__ void hash_tail(uint32_t (&s)[8], const uint8_t *src, 
             }
             if (vb == nvb - 1) { w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
         }
-        compress_rolled<kFma>(s, w, one);
+        compress_rolled<kFma>(s, w, k);
     }
 }
 
@@ -304,7 +310,7 @@ constexpr int kWideThreads = 128;
 template <int kFma, int kStyle>
 __global__ void __launch_bounds__(kWideThreads, kStyle == 4 ? 5 : 1)
 sha256_wide_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *__restrict__ states,
-                   uint32_t *__restrict__ digests, uint32_t one)
+                   uint32_t *__restrict__ digests, FmaK k)
 {
     const uint32_t j = blockIdx.x * kWideThreads + threadIdx.x;
     if (j >= njobs) return;
@@ -312,7 +318,7 @@ sha256_wide_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
     uint32_t s[8];
     load_state(s, states, jb.slot, jb.flags);
 
-    if constexpr (kFma == 2) one = jb.one;          // register operand instead of c[0][..]
+    if constexpr (kFma == 2) k.one = jb.one;        // register operand instead of c[0][..]
     const uint4 *p = reinterpret_cast<const uint4 *>(jb.src);
     uint4 *q = reinterpret_cast<uint4 *>(jb.dst);
     const bool copy = q != nullptr;
@@ -341,14 +347,14 @@ sha256_wide_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
 #pragma unroll
                 for (int i = 0; i < 4; ++i) x[i] = ld_stream(p + i);
             }
-            compress_rolled<kFma>(s, w, one);
+            compress_rolled<kFma>(s, w, k);
             if (copy) {
 #pragma unroll
                 for (int i = 4; i < 8; ++i) st_stream(q + i, x[i]);
                 q += 8;
             }
             unpack_be(w, x[4], x[5], x[6], x[7]);
-            compress_rolled<kFma>(s, w, one);
+            compress_rolled<kFma>(s, w, k);
         }
         rem = (uint32_t)(jb.nbytes & 127u);
     } else if constexpr (kStyle == 0 || kStyle == 2) {
@@ -366,9 +372,9 @@ sha256_wide_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
             p += 8;
             uint32_t w[16];
             unpack_be(w, x[0], x[1], x[2], x[3]);
-            if constexpr (kStyle == 0) compress_regs<kFma>(s, w, one); else compress_rolled<kFma>(s, w, one);
+            if constexpr (kStyle == 0) compress_regs<kFma>(s, w, k); else compress_rolled<kFma>(s, w, k);
             unpack_be(w, x[4], x[5], x[6], x[7]);
-            if constexpr (kStyle == 0) compress_regs<kFma>(s, w, one); else compress_rolled<kFma>(s, w, one);
+            if constexpr (kStyle == 0) compress_regs<kFma>(s, w, k); else compress_rolled<kFma>(s, w, k);
         }
         rem = (uint32_t)(jb.nbytes & 127u);
     } else {
@@ -386,12 +392,12 @@ sha256_wide_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
             p += 4;
             uint32_t w[16];
             unpack_be(w, x[0], x[1], x[2], x[3]);
-            if constexpr (kStyle == 1) compress_regs<kFma>(s, w, one); else compress_rolled<kFma>(s, w, one);
+            if constexpr (kStyle == 1) compress_regs<kFma>(s, w, k); else compress_rolled<kFma>(s, w, k);
         }
         rem = (uint32_t)(jb.nbytes & 63u);
     }
     hash_tail<kFma>(s, reinterpret_cast<const uint8_t *>(p), reinterpret_cast<uint8_t *>(q), rem,
-                    (jb.flags & JOB_FINAL) != 0, jb.total_len, true, one);
+                    (jb.flags & JOB_FINAL) != 0, jb.total_len, true, k);
     store_state(s, states, digests, jb.slot, jb.flags);
 }
 
@@ -405,7 +411,7 @@ constexpr int kKwStride = 68;                 // words per staged block: 64 + 4 
 template <int kFma>
 __global__ void __launch_bounds__(32 * kDeepWarps)
 sha256_deep_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *__restrict__ states,
-                   uint32_t *__restrict__ digests, uint32_t one)
+                   uint32_t *__restrict__ digests, FmaK k)
 {
     __shared__ __align__(16) uint32_t kw_smem[kDeepWarps][32 * kKwStride];
     constexpr uint32_t K[64] = {DM_K256_TABLE};
@@ -417,7 +423,7 @@ sha256_deep_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
     uint32_t s[8];
     load_state(s, states, jb.slot, jb.flags);
     uint32_t *kw = kw_smem[wid];
-    if constexpr (kFma == 2) one = jb.one;
+    if constexpr (kFma == 2) k.one = jb.one;
 
     const uint64_t nblk = jb.nbytes >> 6;
     const uint64_t ngroups = (nblk + 31) >> 5;
@@ -469,14 +475,14 @@ sha256_deep_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
             uint32_t v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = s[i];
-            sha_rounds4<kFma, 0>(v, kp[0], one);   sha_rounds4<kFma, 4>(v, kp[1], one);
-            sha_rounds4<kFma, 8>(v, kp[2], one);   sha_rounds4<kFma, 12>(v, kp[3], one);
-            sha_rounds4<kFma, 16>(v, kp[4], one);  sha_rounds4<kFma, 20>(v, kp[5], one);
-            sha_rounds4<kFma, 24>(v, kp[6], one);  sha_rounds4<kFma, 28>(v, kp[7], one);
-            sha_rounds4<kFma, 32>(v, kp[8], one);  sha_rounds4<kFma, 36>(v, kp[9], one);
-            sha_rounds4<kFma, 40>(v, kp[10], one); sha_rounds4<kFma, 44>(v, kp[11], one);
-            sha_rounds4<kFma, 48>(v, kp[12], one); sha_rounds4<kFma, 52>(v, kp[13], one);
-            sha_rounds4<kFma, 56>(v, kp[14], one); sha_rounds4<kFma, 60>(v, kp[15], one);
+            sha_rounds4<kFma, 0>(v, kp[0], k);   sha_rounds4<kFma, 4>(v, kp[1], k);
+            sha_rounds4<kFma, 8>(v, kp[2], k);   sha_rounds4<kFma, 12>(v, kp[3], k);
+            sha_rounds4<kFma, 16>(v, kp[4], k);  sha_rounds4<kFma, 20>(v, kp[5], k);
+            sha_rounds4<kFma, 24>(v, kp[6], k);  sha_rounds4<kFma, 28>(v, kp[7], k);
+            sha_rounds4<kFma, 32>(v, kp[8], k);  sha_rounds4<kFma, 36>(v, kp[9], k);
+            sha_rounds4<kFma, 40>(v, kp[10], k); sha_rounds4<kFma, 44>(v, kp[11], k);
+            sha_rounds4<kFma, 48>(v, kp[12], k); sha_rounds4<kFma, 52>(v, kp[13], k);
+            sha_rounds4<kFma, 56>(v, kp[14], k); sha_rounds4<kFma, 60>(v, kp[15], k);
 #pragma unroll
             for (int i = 0; i < 8; ++i) s[i] += v[i];
         }
@@ -484,8 +490,117 @@ sha256_deep_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
     }
     const uint64_t done = nblk << 6;
     hash_tail<kFma>(s, jb.src + done, copy ? jb.dst + done : nullptr, (uint32_t)(jb.nbytes & 63u),
-                    (jb.flags & JOB_FINAL) != 0, jb.total_len, lane == 0, one);
+                    (jb.flags & JOB_FINAL) != 0, jb.total_len, lane == 0, k);
     if (lane == 0) store_state(s, states, digests, jb.slot, jb.flags);
+}
+
+// ---------------------------------------------------------------------------
+// group: S streams per warp (S = 2, 4, 8, 16), between deep (S = 1) and wide (S = 32)
+// ---------------------------------------------------------------------------
+// Same two phases as the deep kernel, with the warp's 32 lanes split as
+// lane = b * S + j: stream j, block slot b (B = 32 / S blocks per stream per
+// group).  Phase 1 is fully parallel as before (each lane expands one block);
+// phase 2 runs B dependent block-steps, every lane following stream lane % S,
+// so S round chains advance per instruction instead of one.  Lanes with the
+// same j compute identical values (no divergence); rows of the staged
+// schedule are read as S distinct 16-byte words per LDS.128 (conflict-free for
+// S <= 8, two-way for S = 16).  Streams in a warp may differ in length: a lane
+// simply stops updating its state when its stream has no block in a step.
+template <int kFma, int S>
+__global__ void __launch_bounds__(32)
+sha256_group_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *__restrict__ states,
+                    uint32_t *__restrict__ digests, FmaK k)
+{
+    constexpr uint32_t B = 32 / S;
+    __shared__ __align__(16) uint32_t kw[32 * kKwStride];
+    constexpr uint32_t K[64] = {DM_K256_TABLE};
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t j = lane % S, b = lane / S;
+    const uint32_t job = blockIdx.x * S + j;
+    const bool live = job < njobs;
+    HashJob jb;
+    if (live) jb = load_job(jobs, job);
+    else { jb.src = nullptr; jb.dst = nullptr; jb.nbytes = 0; jb.total_len = 0; jb.slot = 0; jb.flags = JOB_INIT; jb.one = 1; jb.pad_ = 0; }
+    if constexpr (kFma == 2) k.one = jb.one;
+    uint32_t s[8];
+    load_state(s, states, jb.slot, live ? jb.flags : JOB_INIT);
+
+    const uint64_t nblk = jb.nbytes >> 6;                       // this lane's stream
+    uint64_t ngroups = (nblk + B - 1) / B;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {                          // warp-wide max: everyone loops together
+        const uint64_t other = __shfl_xor_sync(0xffffffffu, ngroups, o);
+        ngroups = other > ngroups ? other : ngroups;
+    }
+    const bool copy = jb.dst != nullptr;
+    const uint4 *p = reinterpret_cast<const uint4 *>(jb.src) + 4ull * b;   // block b of group 0
+    uint4 *q = reinterpret_cast<uint4 *>(jb.dst) + 4ull * b;
+
+    uint4 x[4];
+    if (b < nblk) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = ld_stream(p + i);
+    }
+#pragma unroll 1
+    for (uint64_t g = 0; g < ngroups; ++g) {
+        const uint64_t blk0 = g * B;
+        // phase 1: this lane's block (if its stream still has one), schedule + K into row `lane`
+        if (blk0 + b < nblk) {
+            if (copy) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) st_stream(q + i, x[i]);
+            }
+            uint32_t w[16];
+            unpack_be(w, x[0], x[1], x[2], x[3]);
+            uint4 *out = reinterpret_cast<uint4 *>(kw + lane * kKwStride);
+#pragma unroll
+            for (int t = 0; t < 16; t += 4)
+                out[t >> 2] = make_uint4(w[t] + K[t], w[t + 1] + K[t + 1], w[t + 2] + K[t + 2], w[t + 3] + K[t + 3]);
+#pragma unroll
+            for (int t = 16; t < 64; t += 4) {
+#pragma unroll
+                for (int u = t; u < t + 4; ++u)
+                    w[u & 15] += small_sigma1(w[(u - 2) & 15]) + w[(u - 7) & 15] + small_sigma0(w[(u - 15) & 15]);
+                out[t >> 2] = make_uint4(w[t & 15] + K[t], w[(t + 1) & 15] + K[t + 1],
+                                         w[(t + 2) & 15] + K[t + 2], w[(t + 3) & 15] + K[t + 3]);
+            }
+        }
+        __syncwarp();
+        p += 4 * B; q += 4 * B;
+        if (blk0 + B + b < nblk) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = ld_stream(p + i);
+        }
+        // phase 2: B block-steps; lane follows stream j, row = step * S + j
+#pragma unroll 1
+        for (uint32_t st = 0; st < B; ++st) {
+            const bool valid = blk0 + st < nblk;
+            if (__ballot_sync(0xffffffffu, valid) == 0u) break;          // no stream has this step
+            const uint4 *kp = reinterpret_cast<const uint4 *>(kw + (st * S + j) * kKwStride);
+            uint32_t v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = s[i];
+            sha_rounds4<kFma, 0>(v, kp[0], k);   sha_rounds4<kFma, 4>(v, kp[1], k);
+            sha_rounds4<kFma, 8>(v, kp[2], k);   sha_rounds4<kFma, 12>(v, kp[3], k);
+            sha_rounds4<kFma, 16>(v, kp[4], k);  sha_rounds4<kFma, 20>(v, kp[5], k);
+            sha_rounds4<kFma, 24>(v, kp[6], k);  sha_rounds4<kFma, 28>(v, kp[7], k);
+            sha_rounds4<kFma, 32>(v, kp[8], k);  sha_rounds4<kFma, 36>(v, kp[9], k);
+            sha_rounds4<kFma, 40>(v, kp[10], k); sha_rounds4<kFma, 44>(v, kp[11], k);
+            sha_rounds4<kFma, 48>(v, kp[12], k); sha_rounds4<kFma, 52>(v, kp[13], k);
+            sha_rounds4<kFma, 56>(v, kp[14], k); sha_rounds4<kFma, 60>(v, kp[15], k);
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s[i] += v[i];
+            }
+        }
+        __syncwarp();
+    }
+    if (live) {
+        const uint64_t done = nblk << 6;
+        hash_tail<kFma>(s, jb.src + done, copy ? jb.dst + done : nullptr, (uint32_t)(jb.nbytes & 63u),
+                        (jb.flags & JOB_FINAL) != 0, jb.total_len, b == 0, k);
+        if (b == 0) store_state(s, states, digests, jb.slot, jb.flags);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -539,25 +654,27 @@ __global__ void synth_fill_many_kernel(uint64_t seed, uint64_t first_blob, uint8
 
 }  // namespace
 
+static const FmaK kFmaK = {1u, {0u, 0u, 0u}};
+
 template <int kFma, int kStyle>
 static void launch_wide_t(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests, cudaStream_t stream)
 {
     const uint32_t grid = (njobs + kWideThreads - 1) / kWideThreads;
-    sha256_wide_kernel<kFma, kStyle><<<grid, kWideThreads, 0, stream>>>(jobs, njobs, states, digests, 1u);
+    sha256_wide_kernel<kFma, kStyle><<<grid, kWideThreads, 0, stream>>>(jobs, njobs, states, digests, kFmaK);
 }
 
-// variant = fma + 3 * style   (fma 0..2, style 0..4)
+// variant = fma + 4 * style   (fma 0..3, style 0..4)
 cudaError_t launch_sha256_wide(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests,
                                cudaStream_t stream, int variant)
 {
     if (njobs == 0) return cudaSuccess;
     switch (variant) {
-#define DM_W(f, st) case (f) + 3 * (st): launch_wide_t<f, st>(jobs, njobs, states, digests, stream); break;
+#define DM_W(f, st) case (f) + 4 * (st): launch_wide_t<f, st>(jobs, njobs, states, digests, stream); break;
     DM_W(0, 0) DM_W(1, 0) DM_W(2, 0) DM_W(0, 1) DM_W(1, 1) DM_W(2, 1)
     DM_W(0, 2) DM_W(1, 2) DM_W(2, 2) DM_W(0, 3) DM_W(1, 3) DM_W(2, 3)
     DM_W(0, 4) DM_W(1, 4) DM_W(2, 4)
 #undef DM_W
-    default: launch_wide_t<kDefaultWideVariant % 3, kDefaultWideVariant / 3>(jobs, njobs, states, digests, stream); break;
+    default: launch_wide_t<kDefaultWideVariant % 4, kDefaultWideVariant / 4>(jobs, njobs, states, digests, stream); break;
     }
     return cudaGetLastError();
 }
@@ -568,9 +685,26 @@ cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *st
     if (njobs == 0) return cudaSuccess;
     const uint32_t grid = (njobs + kDeepWarps - 1) / kDeepWarps;
     switch (variant) {
-    case 0: sha256_deep_kernel<0><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, 1u); break;
-    case 2: sha256_deep_kernel<2><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, 1u); break;
-    default: sha256_deep_kernel<1><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, 1u); break;
+    case 1: case 3: sha256_deep_kernel<1><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 2: sha256_deep_kernel<2><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    default: sha256_deep_kernel<0><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    }
+    return cudaGetLastError();
+}
+
+// streams_per_warp in {2, 4, 8, 16}
+cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests,
+                                cudaStream_t stream, int streams_per_warp)
+{
+    if (njobs == 0) return cudaSuccess;
+    const uint32_t spw = (uint32_t)streams_per_warp;
+    const uint32_t grid = (njobs + spw - 1) / spw;
+    switch (streams_per_warp) {
+    case 2: sha256_group_kernel<0, 2><<<grid, 32, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 4: sha256_group_kernel<0, 4><<<grid, 32, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 8: sha256_group_kernel<0, 8><<<grid, 32, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 16: sha256_group_kernel<0, 16><<<grid, 32, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }

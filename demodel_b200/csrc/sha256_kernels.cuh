@@ -29,19 +29,31 @@ enum : uint32_t {
 // states/digests: uint32[slot][8], native word order (host serialises big-endian).
 // `digests` may live in mapped pinned host memory.
 // variant (tuning knob, every value is bit-identical): for the wide kernel
-// fma + 3*style, for the deep kernel fma, where fma = how round additions are
-// issued (0 = ptxas' choice, 1 = all on the FMA pipe, 2 = FMA pipe with the
-// shortest e-chain) and style = main-loop shape (see sha256_wide_kernel).
+// fma + 4*style, for the deep kernel fma, where fma = how round additions are
+// issued (0 = ptxas' choice, 1 = all on the FMA pipe, 2 = same with the
+// multiplier in a register) and style = main-loop shape (see sha256_wide_kernel).
 cudaError_t launch_sha256_wide(const HashJob *jobs, uint32_t njobs, uint32_t *states,
                                uint32_t *digests, cudaStream_t stream, int variant);
 cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *states,
                                uint32_t *digests, cudaStream_t stream, int variant);
-constexpr int kDefaultWideVariant = 7;
+constexpr int kDefaultWideVariant = 9;   // fma 1 + style 2
+// S streams per warp, S in {2,4,8,16}: the middle ground between deep and wide.
+cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *states,
+                                uint32_t *digests, cudaStream_t stream, int streams_per_warp);
+
+// Kernel choice by live-stream count: aim for one to two warps on
+// each of the 592 sub-partitions.  Returns streams per warp: 1 = deep, 32 = wide.
+inline int streams_per_warp_for(uint32_t njobs)
+{
+    // crossovers measured on B200 (tools/ab_group.sh, profiles/r01_streams_per_warp_sweep.txt)
+    if (njobs <= 640) return 1;
+    if (njobs <= 3072) return 4;
+    if (njobs <= 6144) return 8;
+    if (njobs <= 12288) return 16;
+    return 32;
+}
 constexpr int kDefaultDeepVariant = 0;
 
-// Live streams below this count go to the warp-per-stream (deep) kernel,
-// above it to the lane-per-stream (wide) kernel; see DESIGN.md §4.
-constexpr uint32_t kDeepWideCrossover = 1024;
 
 cudaError_t launch_synth_fill(uint64_t seed, uint64_t blob, uint64_t byte_off, void *dst,
                               size_t len, cudaStream_t stream);

@@ -219,8 +219,10 @@ class Engine:
             flags |= DM_ING_FORCE_WIDE
         elif kernel == "deep":
             flags |= DM_ING_FORCE_DEEP
+        elif isinstance(kernel, int) and kernel in (1, 2, 4, 8, 16, 32):
+            flags |= (kernel.bit_length()) << 8          # DM_ING_SPW: log2(streams per warp) + 1
         elif kernel is not None:
-            raise ValueError("kernel must be None, 'wide' or 'deep'")
+            raise ValueError("kernel must be None, 'wide', 'deep' or streams-per-warp in {1,2,4,8,16,32}")
         exp = None
         if expect is not None:
             if len(expect) != 32 * n:

@@ -85,6 +85,7 @@ typedef struct dm_stats {
     uint64_t hbm_cas_capacity;
     uint64_t open_streams;
     uint64_t ring_waits;          /* times a writer had to wait for a free ring slab (back-pressure) */
+    uint64_t launches_group;      /* launches of the S-streams-per-warp kernel (counted in kernel_launches) */
 } dm_stats;
 
 /* ---- engine lifetime (start.go:167-216) -------------------------------- */
@@ -169,6 +170,8 @@ int dm_cache_evict(dm_engine *e, const uint8_t digest[32]);   /* HBM tier only; 
 #define DM_ING_REPLACE     0x2u   /* evict an existing blob with the same digest first (benchmarks) */
 #define DM_ING_FORCE_WIDE  0x4u   /* kernel selection override: lane-per-stream */
 #define DM_ING_FORCE_DEEP  0x8u   /* kernel selection override: warp-per-stream */
+#define DM_ING_SPW_SHIFT   8      /* kernel selection override: (log2(streams per warp) + 1) << 8, */
+#define DM_ING_SPW_MASK    0x700u /*   i.e. 1..6 for 1, 2, 4, 8, 16, 32 streams per warp          */
 int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets,
                      const uint64_t *lengths, uint32_t n, const uint8_t *expect, uint8_t *digests_out, uint8_t *matched_out,
                      uint32_t flags, double *kernel_ms);
@@ -177,6 +180,24 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
  * bytes in HBM (e.g. a weight loader on the same GPU).  Returns the number
  * of extents; fills up to max_ext (dev_ptr, len) pairs. */
 int dm_cache_device_extents(dm_engine *e, uint64_t reader, void **dev_ptrs, uint64_t *lens, uint32_t max_ext);
+
+/* ---- manifest-aware prefetch --------------------------- */
+/* An OCI / Ollama image manifest (shape: the reference's cached fixture,
+ * CONTRIBUTING.md:128-153) lists every blob with digest and size before the
+ * bodies are requested. */
+typedef struct dm_layer {
+    uint8_t  digest[32];
+    uint64_t size;
+    char     media_type[96];   /* NUL-terminated, truncated if longer */
+} dm_layer;
+/* Collects every descriptor (object with a "sha256:" digest and an integer
+ * size) in document order: config first, then layers.  *n_layers receives the
+ * total found even if it exceeds max_layers.  DM_EINVAL on malformed JSON. */
+int dm_manifest_parse(const char *json, size_t len, dm_layer *out, uint32_t max_layers, uint32_t *n_layers);
+/* Pre-open one stream per layer that is not already cached, carrying its
+ * expected digest and size (so its extent is reserved and the body is verified
+ * as it arrives).  ids[i] = 0 for layers that are cache hits or duplicates. */
+int dm_manifest_prefetch(dm_engine *e, const dm_layer *layers, uint32_t n, uint64_t *ids);
 
 /* ---- synthetic blob bytes ------------------------------ */
 /* Counter-based generator: byte j of blob `blob` under `seed` is a pure

@@ -1,0 +1,66 @@
+"""dm_manifest_parse on the CPU (the reference's own manifest fixture) and
+dm_manifest_prefetch on the GPU."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+import demodel_b200
+from demodel_b200 import manifest
+
+
+def test_parse_reference_manifest(golden_dir):
+    fx = json.load(open(os.path.join(golden_dir, "reference_fixture.json")))
+    raw = gzip.decompress(bytes.fromhex(fx["gzip_body_hex"]))      # CONTRIBUTING.md:128-153
+    layers = manifest.parse_manifest(raw)
+    assert [(l.digest.hex(), l.size, l.media_type) for l in layers] == [
+        (d["digest"].split(":")[1], d["size"], d["mediaType"]) for d in fx["manifest_layers"]]
+    assert layers[1].size == 274290656 and layers[1].media_type == "application/vnd.ollama.image.model"
+
+
+def test_parse_tolerates_nesting_and_rejects_garbage():
+    d = "ab" * 32
+    doc = {"schemaVersion": 2, "annotations": {"x": {"size": 3, "deep": [1, 2, {"k": None}]}},
+           "config": {"digest": "sha256:" + d, "size": 7, "mediaType": "a/b", "annotations": {"size": "notanumber"}},
+           "layers": [{"size": 1 << 40, "digest": "sha256:" + d.upper(), "platform": {"os": "linux"}},
+                      {"digest": "md5:" + d, "size": 1}, {"digest": "sha256:" + d}, {"size": 1.5, "digest": "sha256:" + d}],
+           "esc": 'q"uote\\ \u00e9 \n'}
+    layers = manifest.parse_manifest(json.dumps(doc).encode())
+    assert [(l.size, l.media_type) for l in layers] == [(7, "a/b"), (1 << 40, "")]
+    assert layers[0].digest == layers[1].digest == bytes.fromhex(d)
+    for bad in (b"", b"{", b'{"a":}', b'{"a":1,}', b'[1,2', b'{"a":1} trailing'):
+        with pytest.raises(demodel_b200.DmError):
+            manifest.parse_manifest(bad)
+    assert manifest.parse_manifest(b"[]") == [] and manifest.parse_manifest(b"{}") == []
+
+
+@pytest.mark.gpu
+def test_prefetch_opens_verified_streams(oracle):
+    bodies = [oracle.blob(0xDE40DE1, 700 + i, 0, n).tobytes() for i, n in enumerate((420, 300000, 11357, 17))]
+    digs = [oracle.sha256(b) for b in bodies]
+    doc = {"schemaVersion": 2, "config": {"mediaType": "application/vnd.docker.container.image.v1+json",
+                                          "digest": "sha256:" + digs[0].hex(), "size": len(bodies[0])},
+           "layers": [{"mediaType": "application/vnd.ollama.image.model", "digest": "sha256:" + d.hex(), "size": len(b)}
+                      for d, b in zip(digs[1:], bodies[1:])] + [
+                     {"mediaType": "dup", "digest": "sha256:" + digs[1].hex(), "size": len(bodies[1])}]}
+    layers = manifest.parse_manifest(json.dumps(doc).encode())
+    assert len(layers) == 5
+    with demodel_b200.Engine(device=0, hbm_cas_bytes=64 << 20, ring_bytes=16 << 20) as eng:
+        ids = manifest.prefetch(eng, layers)
+        assert all(ids[:4]) and ids[4] == 0                  # the duplicate layer shares a stream
+        assert eng.stats()["open_streams"] == 4
+        for sid, body in zip(ids[:4], bodies):
+            eng.stream_write(sid, body)
+        for sid, d in zip(ids[:4], digs):
+            got, ok = eng.stream_finish(sid)
+            assert ok and got == d                           # verified against the manifest's digest
+        assert manifest.prefetch(eng, layers) == [0] * 5     # second pull: everything is a hit
+        # a corrupted layer body is caught by the digest the manifest promised
+        eng.cache_evict(digs[2])
+        ids = manifest.prefetch(eng, layers)
+        assert [bool(i) for i in ids] == [False, False, True, False, False]
+        eng.stream_write(ids[2], bodies[2][:-1] + b"X")
+        got, ok = eng.stream_finish(ids[2])
+        assert not ok and eng.cache_contains(digs[2]) is None
