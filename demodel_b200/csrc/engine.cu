@@ -73,7 +73,8 @@ constexpr int kSlabBatches = 64;           // groups of DMA'd slabs waiting for 
 constexpr int kStripes = 64;               // stream-table lock stripes
 constexpr int kCopyStreams = 2;
 constexpr size_t kBounceBytes = 4u << 20;
-constexpr int kBounces = 8;
+constexpr int kBounces = 48;               // 4 MiB each; readers borrow two as read-ahead windows
+constexpr int kBounceReserve = 4;          // never lent to windows: the spill thread and one-shot reads need some
 
 inline uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
@@ -193,10 +194,16 @@ struct Stream {
     std::shared_ptr<Blob> blob;   // set at commit
 };
 
+struct Bounce;
+struct Window { Bounce *b = nullptr; uint64_t off = 0, len = 0; bool pending = false; };
+
 struct Reader {
     std::shared_ptr<Blob> blob;
     int fd = -1;                  // disk tier
     uint64_t size = 0;
+    std::mutex mu;                // a reader is normally one goroutine; this keeps misuse safe
+    Window win[2];                // double-buffered read-ahead in pinned memory (HBM tier)
+    bool tried_windows = false;
 };
 
 struct Cycle {
@@ -255,7 +262,8 @@ struct dm_engine {
     std::vector<uint32_t> free_slots;
     uint64_t next_id = 1;
     std::unordered_map<Digest, std::shared_ptr<Blob>, DigestHash> blobs;
-    std::unordered_map<uint64_t, std::shared_ptr<Reader>> readers;
+    std::mutex reader_mu[kStripes];
+    std::unordered_map<uint64_t, std::shared_ptr<Reader>> readers[kStripes];
     uint64_t tick = 0;
 
     std::mutex work_mu;              // pump inbox
@@ -826,6 +834,14 @@ Bounce *bounce_get(dm_engine *e)
     e->bounce_free.pop_back();
     return b;
 }
+Bounce *bounce_try_get(dm_engine *e)      // for long-lived borrowers: leaves a reserve
+{
+    std::lock_guard<std::mutex> g(e->bounce_mu);
+    if ((int)e->bounce_free.size() <= kBounceReserve) return nullptr;
+    Bounce *b = e->bounce_free.back();
+    e->bounce_free.pop_back();
+    return b;
+}
 void bounce_put(dm_engine *e, Bounce *b)
 {
     { std::lock_guard<std::mutex> g(e->bounce_mu); e->bounce_free.push_back(b); }
@@ -1001,7 +1017,7 @@ void dm_engine_destroy(dm_engine *e)
     e->spill_cv.notify_all();
     if (e->spiller.joinable()) e->spiller.join();
     cudaDeviceSynchronize();
-    for (auto &kv : e->readers) if (kv.second->fd >= 0) close(kv.second->fd);
+    for (auto &m : e->readers) for (auto &kv : m) if (kv.second->fd >= 0) close(kv.second->fd);
     for (Cycle &c : e->cycles) {
         for (int i = 0; i < kCopyStreams; ++i) if (c.copy_ev[i]) cudaEventDestroy(c.copy_ev[i]);
         if (c.stream) cudaStreamDestroy(c.stream);
@@ -1466,24 +1482,47 @@ int dm_cache_open(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint
         fstat(r->fd, &st);
         r->size = (uint64_t)st.st_size;
     }
-    std::lock_guard<std::mutex> g(e->mu);
-    const uint64_t id = e->next_id++;
-    e->readers[id] = r;
+    uint64_t id;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        id = e->next_id++;
+    }
+    {
+        std::lock_guard<std::mutex> g(e->reader_mu[id % kStripes]);
+        e->readers[id % kStripes][id] = r;
+    }
     *reader = id;
     if (size) *size = r->size;
     return DM_OK;
 }
 
+static std::shared_ptr<Reader> find_reader(dm_engine *e, uint64_t id)
+{
+    std::lock_guard<std::mutex> g(e->reader_mu[id % kStripes]);
+    auto it = e->readers[id % kStripes].find(id);
+    return it == e->readers[id % kStripes].end() ? nullptr : it->second;
+}
+
+// Start the D2H of [start, start + <=4 MiB) of the blob into a read-ahead window.
+static cudaError_t window_fill(dm_engine *e, Reader *r, Window &w, uint64_t start)
+{
+    const uint64_t n = std::min<uint64_t>(kBounceBytes, r->size - start);
+    uint8_t *dst = w.b->host;
+    cudaError_t err = cudaSuccess;
+    for_segments(e, r->blob->extents, start, n, [&](uint8_t *dev, uint64_t l) {
+        if (err == cudaSuccess) err = cudaMemcpyAsync(dst, dev, l, cudaMemcpyDeviceToHost, w.b->stream);
+        dst += l;
+    });
+    w.off = start; w.len = n; w.pending = true;
+    e->st_d2h += n;
+    return err;
+}
+
 int dm_cache_read(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t len, size_t *nread)
 {
     if (!e || (!buf && len)) return fail(DM_EINVAL, "null argument");
-    std::shared_ptr<Reader> r;
-    {
-        std::lock_guard<std::mutex> g(e->mu);
-        auto it = e->readers.find(reader);
-        if (it == e->readers.end()) return fail(DM_EINVAL, "unknown reader id");
-        r = it->second;
-    }
+    std::shared_ptr<Reader> r = find_reader(e, reader);
+    if (!r) return fail(DM_EINVAL, "unknown reader id");
     if (nread) *nread = 0;
     if (off > r->size) return fail(DM_ERANGE, "offset beyond blob end");
     len = (size_t)std::min<uint64_t>(len, r->size - off);
@@ -1502,24 +1541,68 @@ int dm_cache_read(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t
         return DM_OK;
     }
     cudaSetDevice(e->device);
-    Bounce *bn = bounce_get(e);
+    std::lock_guard<std::mutex> g(r->mu);
+    if (!r->tried_windows) {
+        r->tried_windows = true;
+        Bounce *a = bounce_try_get(e), *b = a ? bounce_try_get(e) : nullptr;
+        if (a && b) { r->win[0].b = a; r->win[1].b = b; }
+        else if (a) bounce_put(e, a);
+    }
     size_t done = 0;
     int rc = DM_OK;
-    while (done < len) {
-        const size_t n = std::min(len - done, kBounceBytes);
-        uint8_t *dst = bn->host;
-        cudaError_t err = cudaSuccess;
-        for_segments(e, r->blob->extents, off + done, n, [&](uint8_t *dev, uint64_t l) {
-            if (err == cudaSuccess) err = cudaMemcpyAsync(dst, dev, l, cudaMemcpyDeviceToHost, bn->stream);
-            dst += l;
-        });
-        if (err == cudaSuccess) err = cudaStreamSynchronize(bn->stream);
-        if (err != cudaSuccess) { rc = fail_cuda(err, "cudaMemcpyAsync(D2H)"); break; }
-        memcpy(out + done, bn->host, n);
-        done += n;
+    if (r->win[0].b) {
+        // HTTP bodies are read front to back in small pieces (io.Copy: 32 KiB): serve them from two
+        // 4 MiB pinned windows, the next one filling by DMA while this one is copied out.
+        while (done < len) {
+            const uint64_t pos = off + done;
+            Window *w = nullptr;
+            for (Window &c : r->win) if (c.len && pos >= c.off && pos < c.off + c.len) w = &c;
+            cudaError_t err = cudaSuccess;
+            if (!w) {                                              // miss: restart the pipeline at pos
+                for (Window &c : r->win) if (c.pending) { cudaStreamSynchronize(c.b->stream); c.pending = false; }
+                err = window_fill(e, r.get(), r->win[0], pos);
+                r->win[1].len = 0;
+                if (err == cudaSuccess && pos + r->win[0].len < r->size)
+                    err = window_fill(e, r.get(), r->win[1], pos + r->win[0].len);
+                if (err != cudaSuccess) { rc = fail_cuda(err, "cudaMemcpyAsync(D2H)"); break; }
+                w = &r->win[0];
+            }
+            if (w->pending) {
+                err = cudaStreamSynchronize(w->b->stream);
+                w->pending = false;
+                if (err != cudaSuccess) { rc = fail_cuda(err, "cudaStreamSynchronize(D2H)"); break; }
+            }
+            const size_t n = (size_t)std::min<uint64_t>(len - done, w->off + w->len - pos);
+            memcpy(out + done, w->b->host + (pos - w->off), n);
+            done += n;
+            if (pos + n == w->off + w->len) {                      // window drained: refill it behind the other one
+                Window &other = (w == &r->win[0]) ? r->win[1] : r->win[0];
+                const uint64_t next = other.len ? other.off + other.len : w->off + w->len;
+                if (next < r->size && other.len && other.off == w->off + w->len) {
+                    err = window_fill(e, r.get(), *w, next);
+                    if (err != cudaSuccess) { rc = fail_cuda(err, "cudaMemcpyAsync(D2H)"); break; }
+                } else w->len = 0;
+            }
+        }
+    } else {
+        Bounce *bn = bounce_get(e);                                // no windows left: one-shot staging
+        while (done < len) {
+            const size_t n = std::min(len - done, kBounceBytes);
+            uint8_t *dst = bn->host;
+            cudaError_t err = cudaSuccess;
+            for_segments(e, r->blob->extents, off + done, n, [&](uint8_t *dev, uint64_t l) {
+                if (err == cudaSuccess) err = cudaMemcpyAsync(dst, dev, l, cudaMemcpyDeviceToHost, bn->stream);
+                dst += l;
+            });
+            if (err == cudaSuccess) err = cudaStreamSynchronize(bn->stream);
+            if (err != cudaSuccess) { rc = fail_cuda(err, "cudaMemcpyAsync(D2H)"); break; }
+            memcpy(out + done, bn->host, n);
+            done += n;
+            e->st_d2h += n;
+        }
+        bounce_put(e, bn);
     }
-    bounce_put(e, bn);
-    e->st_d2h += done; e->st_served += done;
+    e->st_served += done;
     if (nread) *nread = done;
     return rc;
 }
@@ -1529,12 +1612,24 @@ int dm_cache_close(dm_engine *e, uint64_t reader)
     if (!e) return fail(DM_EINVAL, "null argument");
     std::shared_ptr<Reader> r;
     {
-        std::lock_guard<std::mutex> g(e->mu);
-        auto it = e->readers.find(reader);
-        if (it == e->readers.end()) return fail(DM_EINVAL, "unknown reader id");
+        std::lock_guard<std::mutex> g(e->reader_mu[reader % kStripes]);
+        auto it = e->readers[reader % kStripes].find(reader);
+        if (it == e->readers[reader % kStripes].end()) return fail(DM_EINVAL, "unknown reader id");
         r = it->second;
-        e->readers.erase(it);
-        if (r->blob) r->blob->readers--;
+        e->readers[reader % kStripes].erase(it);
+    }
+    {
+        std::lock_guard<std::mutex> g(r->mu);
+        for (Window &w : r->win) {
+            if (!w.b) continue;
+            if (w.pending) cudaStreamSynchronize(w.b->stream);
+            bounce_put(e, w.b);
+            w.b = nullptr;
+        }
+    }
+    if (r->blob) {
+        std::lock_guard<std::mutex> g(e->mu);
+        r->blob->readers--;
     }
     if (r->fd >= 0) close(r->fd);
     return DM_OK;
@@ -1562,12 +1657,11 @@ int dm_cache_evict(dm_engine *e, const uint8_t digest[32])
 int dm_cache_device_extents(dm_engine *e, uint64_t reader, void **dev_ptrs, uint64_t *lens, uint32_t max_ext)
 {
     if (!e) return fail(DM_EINVAL, "null argument");
-    std::lock_guard<std::mutex> g(e->mu);
-    auto it = e->readers.find(reader);
-    if (it == e->readers.end()) return fail(DM_EINVAL, "unknown reader id");
-    if (!it->second->blob) return fail(DM_ESTATE, "blob is on the disk tier only");
-    const auto &ext = it->second->blob->extents;
-    uint64_t left = it->second->blob->size;
+    std::shared_ptr<Reader> r = find_reader(e, reader);
+    if (!r) return fail(DM_EINVAL, "unknown reader id");
+    if (!r->blob) return fail(DM_ESTATE, "blob is on the disk tier only");
+    const auto &ext = r->blob->extents;
+    uint64_t left = r->blob->size;
     for (uint32_t i = 0; i < ext.size() && i < max_ext; ++i) {
         if (dev_ptrs) dev_ptrs[i] = e->arena_base + ext[i].off;
         if (lens) lens[i] = std::min(left, ext[i].len);
