@@ -406,6 +406,8 @@ def main():
         if os.path.exists(tpath):
             try:
                 traffic = json.load(open(tpath)).get(args.workload)
+                if args.hash_only or args.kernel:
+                    traffic = None          # the capture is of the default mode only
             except Exception:
                 traffic = None
         line = {
