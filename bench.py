@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-serve", action="store_true")
+    ap.add_argument("--no-probes", action="store_true", help="skip the short many-stream kernel probes")
     ap.add_argument("--e2e-zero-copy", action="store_true")
     ap.add_argument("--ring-mib", type=int, default=1024)
     ap.add_argument("--slab-kib", type=int, default=1024)
@@ -256,7 +257,7 @@ def main():
     hbm_peak, peak_src = _peaks()
 
     cas_bytes = 0 if args.hash_only else span + (64 << 20)
-    eng = demodel_b200.Engine(device=local, hbm_cas_bytes=max(cas_bytes, 256 << 20) + (2 << 30), ring_bytes=args.ring_mib << 20,
+    eng = demodel_b200.Engine(device=local, hbm_cas_bytes=max(cas_bytes, 256 << 20) + (4 << 30), ring_bytes=args.ring_mib << 20,
                               slab_bytes=args.slab_kib << 10, max_streams=max(65536, n + 1024))
     dev = torch.empty(span, dtype=torch.uint8, device=f"cuda:{local}")
     # blob indices are consecutive per rank only when world == 1; fill one by one otherwise
@@ -308,6 +309,35 @@ def main():
     probe = min(range(n), key=lambda i: sizes[i])
     host_probe = dev[offs[probe]:offs[probe] + sizes[probe]].cpu().numpy()
     assert hashlib.sha256(host_probe.tobytes()).digest() == digs[probe], "GPU digest differs from hashlib"
+
+    # ---- probes: the other kernel shapes at stream counts that fill the chip (kernel time only) ----
+    probes = None
+    if rank == 0 and not args.no_probes and args.blobs == 0:
+        probes = {}
+        for name, pn, pbytes in (("wide_151552_streams", 151552, 16384), ("group8_4096_streams", 4096, 524288)):
+            po = np.arange(pn, dtype=np.uint64) * np.uint64(pbytes)
+            pl = np.full(pn, pbytes, dtype=np.uint64)
+            pdev = torch.empty(pn * pbytes, dtype=torch.uint8, device=f"cuda:{local}")
+            eng.synth_fill_device_many(SEED, 1 << 20, pdev.data_ptr(), po, pl)
+            pd, _, _ = eng.ingest_device(pdev.data_ptr(), po, pl, hash_only=True, raw=True)
+            pexp = pd.tobytes()
+            kms = []
+            for it in range(8):
+                _, pm, ms_ = eng.ingest_device(pdev.data_ptr(), po, pl, expect=pexp, replace=True, raw=True)
+                assert pm.all()
+                if it >= 3:
+                    kms.append(ms_)
+            k_ms = sum(kms) / len(kms)
+            ach = 2 * pn * pbytes / (k_ms / 1e3) / 1e9
+            probes[name] = {"streams": pn, "blob_bytes": pbytes, "kernel_ms": k_ms, "hashed_GBps": ach / 2,
+                            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                                         "frac": ach / hbm_peak, "algorithmic_bytes_per_blob_byte": 2},
+                            "alu_issue_bound_GBps": 1146.0, "frac_of_alu_bound": ach / 2 / 1146.0}
+            import ctypes as _C
+            lib_ = demodel_b200.load()
+            for i_ in range(pn):                                # drop the probe's blobs from the CAS
+                lib_.dm_cache_evict(eng._h, _C.c_char_p(pexp[32 * i_:32 * i_ + 32]))
+            del pdev
 
     # ---- e2e leg: host buffers through the proxy-facing C-ABI ---------------------------
     e2e = None
@@ -422,7 +452,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_blob_byte": bytes_per_blob_byte, "kernel_ms_per_step": kernel_ms_max / args.steps},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "probes": probes,
             "host": {"cpus": os.cpu_count(), "cpu_quota": _cpu_quota(), "kernel_variant": os.environ.get("DM_KERNEL_VARIANT")},
         }
         print(json.dumps(line), flush=True)

@@ -614,6 +614,71 @@ std::shared_ptr<Blob> publish(dm_engine *e, const Digest &d, uint64_t size, std:
     return b;
 }
 
+// Batch form of publish() for dm_ingest_device: every blob has exactly one right-sized extent, so
+// the index is updated under ONE lock and the arena under one more (150 k blobs per call otherwise
+// spend longer in lock traffic than in the kernel).
+struct Verified { Digest d; uint64_t size; Extent x; };
+void publish_many(dm_engine *e, const std::vector<Verified> &items)
+{
+    std::vector<Extent> to_free;
+    std::vector<std::shared_ptr<Blob>> to_spill;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        for (const Verified &v : items) {
+            auto it = e->blobs.find(v.d);
+            if (it != e->blobs.end() && it->second->in_hbm) {          // an earlier copy wins
+                it->second->tick = ++e->tick;
+                to_free.push_back(v.x);
+            } else if (it != e->blobs.end()) {                         // on disk only: re-home
+                Blob *b = it->second.get();
+                b->extents.assign(1, v.x);
+                b->in_hbm = true; b->tick = ++e->tick;
+            } else {
+                auto b = std::make_shared<Blob>();
+                b->digest = v.d; b->size = v.size; b->extents.assign(1, v.x);
+                b->in_hbm = true; b->tick = ++e->tick;
+                e->blobs.emplace(v.d, b);
+                if (!e->cas_dir.empty()) to_spill.push_back(b);
+            }
+        }
+    }
+    e->st_committed += items.size();
+    if (!to_free.empty()) {
+        std::lock_guard<std::mutex> g(e->arena_mu);
+        for (const Extent &x : to_free) e->arena.release(x.off, x.len);
+    }
+    if (!to_spill.empty()) {
+        {
+            std::lock_guard<std::mutex> g(e->spill_mu);
+            for (auto &b : to_spill) e->spill_q.push_back(b);
+        }
+        e->spill_cv.notify_one();
+    }
+}
+
+// Batch eviction (DM_ING_REPLACE): drop the HBM copies of these digests under one lock each way.
+void evict_many(dm_engine *e, const uint8_t *digests, uint32_t n)
+{
+    std::vector<std::shared_ptr<Blob>> victims;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        for (uint32_t i = 0; i < n; ++i) {
+            Digest d;
+            memcpy(d.b, digests + 32ull * i, 32);
+            auto it = e->blobs.find(d);
+            if (it == e->blobs.end() || !it->second->in_hbm || it->second->readers) continue;
+            it->second->in_hbm = false;
+            victims.push_back(it->second);
+            if (!it->second->on_disk) e->blobs.erase(it);
+        }
+    }
+    std::lock_guard<std::mutex> g(e->arena_mu);
+    for (auto &b : victims) {
+        for (const Extent &x : b->extents) e->arena.release(x.off, x.len);
+        b->extents.clear();
+    }
+}
+
 // ---- pump ----------------------------------------------------------------------
 
 void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint32_t *words)
@@ -1687,22 +1752,36 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
     int rc = ensure_ingest_scratch(e, n);
     if (rc != DM_OK) return rc;
     const bool hash_only = (flags & DM_ING_HASH_ONLY) != 0;
-    std::vector<std::vector<Extent>> ext(n);
-    auto cleanup = [&] { for (auto &v : ext) if (!v.empty()) free_extents(e, v); };
-    if ((flags & DM_ING_REPLACE) && expect && !hash_only)
-        for (uint32_t i = 0; i < n; ++i) dm_cache_evict(e, expect + 32ull * i);
+    std::vector<Extent> ext(hash_only ? 0 : n, Extent{0, 0});
+    auto cleanup = [&] {
+        std::lock_guard<std::mutex> g(e->arena_mu);
+        for (const Extent &x : ext) e->arena.release(x.off, x.len);
+    };
+    if ((flags & DM_ING_REPLACE) && expect && !hash_only) evict_many(e, expect, n);
     const uint8_t *base = static_cast<const uint8_t *>(dev_base);
     uint64_t total = 0;
+    uint32_t allocated = 0;
+    if (!hash_only) {                                   // fast path: all extents under one arena lock
+        std::lock_guard<std::mutex> g(e->arena_mu);
+        for (; allocated < n; ++allocated) {
+            const uint64_t want = round_up(std::max<uint64_t>(lengths[allocated], 1), kAlign);
+            uint64_t off;
+            if (!e->arena.alloc(want, &off)) break;
+            ext[allocated] = Extent{off, want};
+        }
+    }
     for (uint32_t i = 0; i < n; ++i) {
         const uint64_t len = lengths[i];
         dm::HashJob &jb = e->ing_jobs_h[i];
         jb.src = base + offsets[i]; jb.dst = nullptr; jb.nbytes = len; jb.total_len = len;
         jb.slot = i; jb.flags = dm::JOB_INIT | dm::JOB_FINAL; jb.one = 1; jb.pad_ = 0;
         if (!hash_only) {
-            Extent x;
-            if (!arena_alloc(e, len, &x)) { cleanup(); return fail(DM_ENOMEM, "HBM CAS arena exhausted"); }
-            ext[i].push_back(x);
-            jb.dst = e->arena_base + x.off;
+            if (i >= allocated) {                       // arena full: evict LRU blobs one allocation at a time
+                Extent x;
+                if (!arena_alloc(e, len, &x)) { cleanup(); return fail(DM_ENOMEM, "HBM CAS arena exhausted"); }
+                ext[i] = x;
+            }
+            jb.dst = e->arena_base + ext[i].off;
         }
         total += len;
     }
@@ -1736,6 +1815,9 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
     { std::lock_guard<std::mutex> g(e->stat_mu); e->st_kernel_ms += ms; }
     e->st_launches++; (spw == 1 ? e->st_deep : spw == 32 ? e->st_wide : e->st_group)++;
     e->st_hashed += total;
+    std::vector<Verified> good;
+    std::vector<Extent> bad;
+    if (!hash_only) good.reserve(n);
     for (uint32_t i = 0; i < n; ++i) {
         Digest d;
         words_to_digest(e->ing_digests_h + 8ull * i, d.b);
@@ -1743,8 +1825,13 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
         const int ok = (!expect || memcmp(expect + 32ull * i, d.b, 32) == 0) ? 1 : 0;
         if (matched_out) matched_out[i] = (uint8_t)ok;
         if (hash_only) continue;
-        if (ok) publish(e, d, lengths[i], ext[i]);
-        else { free_extents(e, ext[i]); e->st_mismatch++; }
+        if (ok) good.push_back(Verified{d, lengths[i], ext[i]});
+        else { bad.push_back(ext[i]); e->st_mismatch++; }
+    }
+    if (!good.empty()) publish_many(e, good);
+    if (!bad.empty()) {
+        std::lock_guard<std::mutex> g(e->arena_mu);
+        for (const Extent &x : bad) e->arena.release(x.off, x.len);
     }
     return DM_OK;
 }
