@@ -352,7 +352,8 @@ def main():
         ncpu_eff = int(_cpu_quota() or os.cpu_count() or 1)
         # GOMAXPROCS-style worker threads; half the usable cores measured best (the pump thread, the
         # CUDA driver's threads and the DMA submissions share the same cgroup quota)
-        drive_threads = max(1, min(conc, args.e2e_threads or max(1, ncpu_eff // 2)))
+        # ... and the ranks of one node share it, so each takes its 1/world share.
+        drive_threads = max(1, min(conc, args.e2e_threads or max(1, ncpu_eff // (2 * world))))
         e2e_steps = max(1, min(args.steps, 3))
         for _ in range(1):
             dd, mm, _ = eng.proxy_drive(host, hoff, expect=expect, chunk=32768, concurrency=conc,
