@@ -1495,8 +1495,15 @@ int dm_stream_abort(dm_engine *e, uint64_t id)
         s->st = St::Aborted;
         free_now = s->jobs_inflight == 0;
     }
-    if (free_now) free_extents(e, s->extents);
-    drop_stream(e, sp, free_now);   // otherwise the pump releases slot + extents at reap
+    if (free_now) {
+        // A slab DMA into this extent may still be in flight; the range must not be handed to
+        // another blob before it lands (the stale copy would overwrite the new owner's bytes).
+        cudaSetDevice(e->device);
+        cudaStreamSynchronize(e->copy_stream[s->id % kCopyStreams]);
+        free_extents(e, s->extents);
+    }
+    drop_stream(e, sp, free_now);   // otherwise the pump releases slot + extents at reap (after the kernel,
+                                    // which itself waited for every DMA enqueued before its launch)
     s->cv.notify_all();
     return DM_OK;
 }

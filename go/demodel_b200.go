@@ -268,3 +268,83 @@ func (r *HitReader) Read(p []byte) (int, error) {
 func (r *HitReader) Close() error {
 	return check(C.dm_cache_close(r.e, r.id))
 }
+
+// ---- Range parts, checkpoint / resume, manifest prefetch (source only, see header note) ----
+
+// WriteAt feeds one piece of a `Range:` response into the stream that owns the
+// blob; parts may arrive in any order (dm_stream_write_at).
+func (t *BodyTee) WriteAt(p []byte, off int64) (int, error) {
+	if len(p) == 0 {
+		return 0, nil
+	}
+	if err := check(C.dm_stream_write_at(t.e, t.id, C.uint64_t(off), unsafe.Pointer(&p[0]), C.size_t(len(p)))); err != nil {
+		return 0, err
+	}
+	return len(p), nil
+}
+
+// Checkpoint is the SHA-256 mid-state of an interrupted download.
+type Checkpoint struct {
+	H     [8]uint32
+	Bytes uint64
+}
+
+// Checkpoint waits until every whole block received in order is hashed.
+func (t *BodyTee) Checkpoint() (Checkpoint, error) {
+	var ck C.dm_checkpoint
+	if err := check(C.dm_stream_checkpoint(t.e, t.id, &ck)); err != nil {
+		return Checkpoint{}, err
+	}
+	out := Checkpoint{Bytes: uint64(ck.bytes)}
+	for i := range out.H {
+		out.H[i] = uint32(ck.h[i])
+	}
+	return out, nil
+}
+
+// Resume continues a blob from a checkpoint when the client retries with
+// `Range: bytes=<ck.Bytes>-`.
+func Resume(p *Pool, up io.ReadCloser, ck Checkpoint, expect *[32]byte, contentLength int64) (*BodyTee, error) {
+	t := &BodyTee{e: p.engineFor(expect), up: up}
+	var c C.dm_checkpoint
+	for i := range ck.H {
+		c.h[i] = C.uint32_t(ck.H[i])
+	}
+	c.bytes = C.uint64_t(ck.Bytes)
+	c.abi = C.DM_ABI_VERSION
+	if err := check(C.dm_stream_resume(t.e, &c, (*C.uint8_t)(unsafe.Pointer(&expect[0])), C.uint64_t(contentLength), &t.id)); err != nil {
+		return nil, err
+	}
+	t.open = true
+	return t, nil
+}
+
+// Layer is one descriptor of an OCI / Ollama manifest.
+type Layer struct {
+	Digest    [32]byte
+	Size      uint64
+	MediaType string
+}
+
+// ParseManifest lists config + layers of a manifest body (the shape of the
+// reference's cached fixture, CONTRIBUTING.md:128-153).
+func ParseManifest(body []byte) ([]Layer, error) {
+	if len(body) == 0 {
+		return nil, &Error{Code: int(C.DM_EINVAL), Detail: "empty manifest"}
+	}
+	var n C.uint32_t
+	raw := make([]C.dm_layer, 64)
+	if err := check(C.dm_manifest_parse((*C.char)(unsafe.Pointer(&body[0])), C.size_t(len(body)), &raw[0], 64, &n)); err != nil {
+		return nil, err
+	}
+	if int(n) > len(raw) {
+		n = C.uint32_t(len(raw))
+	}
+	out := make([]Layer, int(n))
+	for i := range out {
+		copy(out[i].Digest[:], C.GoBytes(unsafe.Pointer(&raw[i].digest[0]), 32))
+		out[i].Size = uint64(raw[i].size)
+		out[i].MediaType = C.GoString(&raw[i].media_type[0])
+	}
+	return out, nil
+}
