@@ -64,3 +64,52 @@ def test_prefetch_opens_verified_streams(oracle):
         eng.stream_write(ids[2], bodies[2][:-1] + b"X")
         got, ok = eng.stream_finish(ids[2])
         assert not ok and eng.cache_contains(digs[2]) is None
+
+
+@pytest.mark.gpu
+def test_ollama_pull_at_the_fixture_sizes(oracle, golden_dir):
+    """BASELINE configs[3] in miniature: the reference's manifest (CONTRIBUTING.md:128-153) with its
+    real layer sizes (one 274 MB model layer + three small blobs), synthetic bytes, digests substituted,
+    sharded over however many GPUs are visible by digest prefix, pulled through pre-opened streams."""
+    import hashlib
+    import threading
+    fx = json.load(open(os.path.join(golden_dir, "reference_fixture.json")))
+    sizes = [l["size"] for l in fx["manifest_layers"]]
+    assert sizes == [420, 274290656, 11357, 17]
+    bodies = [demodel_b200.synth_fill_host(0xDE40DE1, 900 + i, 0, n) for i, n in enumerate(sizes)]
+    digs = [hashlib.sha256(b.tobytes()).digest() for b in bodies]
+    doc = json.loads(gzip.decompress(bytes.fromhex(fx["gzip_body_hex"])))
+    doc["config"]["digest"] = "sha256:" + digs[0].hex()
+    for layer, d in zip(doc["layers"], digs[1:]):
+        layer["digest"] = "sha256:" + d.hex()
+    layers = manifest.parse_manifest(json.dumps(doc).encode())
+    assert [l.size for l in layers] == sizes and [l.digest for l in layers] == digs
+    ngpu = demodel_b200.load().dm_device_count()
+    engines = [demodel_b200.Engine(device=g, hbm_cas_bytes=512 << 20, ring_bytes=64 << 20) for g in range(ngpu)]
+    try:
+        home = [demodel_b200.shard_of(l.digest, ngpu) for l in layers]
+        ids = {}
+        for g, eng in enumerate(engines):
+            mine = [l for l, h in zip(layers, home) if h == g]
+            for l, sid in zip(mine, manifest.prefetch(eng, mine)):
+                ids[l.digest] = (eng, sid)
+        results = {}
+
+        def pull(i):                                   # one goroutine per layer
+            eng, sid = ids[digs[i]]
+            for off in range(0, sizes[i], 1 << 20):
+                eng.stream_write(sid, bodies[i][off:off + (1 << 20)])
+            results[i] = eng.stream_finish(sid)
+        ths = [threading.Thread(target=pull, args=(i,)) for i in range(4)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join(timeout=120)
+        assert all(results[i] == (digs[i], True) for i in range(4))
+        eng, _ = ids[digs[1]]
+        rid, size = eng.cache_open(digs[1])            # the model layer is a hit now, on its home GPU
+        assert size == sizes[1] and eng.cache_read(rid, size - 4096, 4096) == bodies[1][-4096:].tobytes()
+        eng.cache_close(rid)
+    finally:
+        for e in engines:
+            e.close()
