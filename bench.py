@@ -339,6 +339,21 @@ def main():
                 lib_.dm_cache_evict(eng._h, _C.c_char_p(pexp[32 * i_:32 * i_ + 32]))
             del pdev
 
+    # small-blob latency through the stream API: open -> write 4 KiB -> finish (DMA + launch + digest back)
+    if probes is not None:
+        small = np.frombuffer(os.urandom(4096), dtype=np.uint8)
+        lat = []
+        for it in range(220):
+            t0_ = time.perf_counter()
+            sid_ = eng.stream_open(None, 4096)
+            eng.stream_write(sid_, small)
+            d_, _ = eng.stream_finish(sid_)
+            lat.append(time.perf_counter() - t0_)
+            eng.cache_evict(d_)
+        lat = sorted(lat[20:])
+        probes["small_blob_latency_us"] = {"p50": 1e6 * lat[len(lat) // 2], "p99": 1e6 * lat[int(len(lat) * 0.99)],
+                                          "what": "dm_stream_open + write(4 KiB) + finish, one at a time, via ctypes"}
+
     # ---- e2e leg: host buffers through the proxy-facing C-ABI ---------------------------
     e2e = None
     if not args.no_e2e:
