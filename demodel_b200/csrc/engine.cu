@@ -157,7 +157,7 @@ struct Blob {
     bool spill_done = false;
 };
 
-struct Slab { uint8_t *host; };
+struct Slab { uint8_t *host; uint8_t *dev; };   // dev: same slab of the device-side mirror (verify-only streams)
 
 enum class St { Open, Finishing, Done, Aborted };
 
@@ -183,6 +183,11 @@ struct Stream {
     uint64_t resume_base = 0;                    // bytes hashed before this stream existed (checkpoint)
     std::map<uint64_t, uint64_t> prefix_cover;   // what of [0, resume_base) was re-supplied for caching
     bool ckpt_waiter = false;
+    // Verify-only streams (DM_F_NO_HBM_CAS, or a blob that could never fit the arena): nothing is
+    // retained.  Slabs are DMA'd to the device mirror of the ring and hashed from there, one slab per
+    // job in arrival order; a slab returns to the ring when its job has run.
+    bool verify_only = false;
+    std::deque<std::pair<Slab *, uint32_t>> staged;
     bool window_out = false;   // acquire() window outstanding
     bool queued = false;       // in the pump's inbox / ready list (guarded by mu)
     bool final_issued = false;
@@ -217,6 +222,7 @@ struct Cycle {
     bool deep = false;
     uint64_t bytes = 0;
     std::vector<std::shared_ptr<Stream>> streams;   // one entry per job
+    std::vector<Slab *> job_slabs;                  // verify-only jobs: the ring slab to release at reap
     std::vector<uint8_t> is_final;
 };
 
@@ -246,6 +252,7 @@ struct dm_engine {
     Arena arena;
 
     uint8_t *ring = nullptr;
+    uint8_t *dev_ring = nullptr;     // device mirror of the ring, allocated on first verify-only use
     std::vector<Slab> slab_store;
     std::mutex slab_mu;
     std::condition_variable slab_cv;
@@ -504,6 +511,16 @@ int submit_slab(dm_engine *e, const std::shared_ptr<Stream> &sp)
     const uint32_t n = s->cur_fill;
     s->cur = nullptr; s->cur_fill = 0;
     if (n == 0) { slab_put(e, slab); return DM_OK; }
+    if (s->verify_only) {
+        cudaSetDevice(e->device);
+        cudaError_t err = cudaMemcpyAsync(slab->dev, slab->host, n, cudaMemcpyHostToDevice, e->copy_stream[s->id % kCopyStreams]);
+        if (err != cudaSuccess) { slab_put(e, slab); return fail_cuda(err, "cudaMemcpyAsync(H2D slab)"); }
+        e->st_h2d += n;
+        s->staged.emplace_back(slab, n);
+        s->dma_issued += n;
+        mark_dirty(e, sp, nullptr);       // the slab stays out of the ring until its job has run
+        return DM_OK;
+    }
     int rc = dma_range(e, sp, slab, s->dma_issued, n);
     if (rc != DM_OK) return rc;
     s->dma_issued += n;
@@ -700,7 +717,7 @@ void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint
                         s->prefix_cover.begin()->second >= s->resume_base);
     g.unlock();
     std::shared_ptr<Blob> b;
-    if (matched && whole) b = publish(e, d, size, ext);
+    if (matched && whole && !s->verify_only) b = publish(e, d, size, ext);
     else { free_extents(e, ext); if (!matched) e->st_mismatch++; }
     g.lock();
     s->blob = b;
@@ -718,6 +735,8 @@ void reap_cycle(dm_engine *e, Cycle &c)
         e->st_kernel_ms += ms;
     }
     e->st_hashed += c.bytes;
+    for (Slab *sl : c.job_slabs) if (sl) slab_put(e, sl);
+    c.job_slabs.clear();
     for (size_t i = 0; i < c.streams.size(); ++i) {
         std::shared_ptr<Stream> &sp = c.streams[i];
         bool free_now = false, wake = false;
@@ -760,10 +779,24 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
         uint64_t n = finishing ? (s->dma_issued - s->hash_issued) : ((s->dma_issued - s->hash_issued) & ~63ull);
         if (!finishing && n == 0) { s->queued = false; continue; }
         uint64_t contig = 0;
-        uint8_t *src = n ? seg_at(e, s->extents, s->hash_issued, &contig) : nullptr;
+        uint8_t *src = nullptr;
         bool final = finishing;
-        if (n > contig && n) { n = contig; final = false; }          // stop at the extent boundary
-        if (n > quantum) { n = quantum; final = false; }
+        Slab *job_slab = nullptr;
+        if (s->verify_only) {
+            if (!s->staged.empty()) {
+                job_slab = s->staged.front().first;
+                n = s->staged.front().second;               // whole slab; only the last may hold a partial block
+                src = job_slab->dev;
+                s->staged.pop_front();
+                final = finishing && s->staged.empty();
+                if (!final && (n & 63)) { final = false; }   // cannot happen: mid-stream slabs are full
+            } else if (!finishing) { s->queued = false; continue; }
+            else n = 0;
+        } else {
+            src = n ? seg_at(e, s->extents, s->hash_issued, &contig) : nullptr;
+            if (n > contig && n) { n = contig; final = false; }          // stop at the extent boundary
+            if (n > quantum) { n = quantum; final = false; }
+        }
         dm::HashJob &jb = c.h_jobs[c.njobs++];
         jb.src = src; jb.dst = nullptr; jb.nbytes = n; jb.total_len = s->dma_issued; jb.slot = s->slot;
         jb.flags = (s->hash_issued == 0 ? dm::JOB_INIT : 0u) | (final ? dm::JOB_FINAL : 0u);
@@ -774,7 +807,8 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
         c.bytes += n;
         c.streams.push_back(sp);
         c.is_final.push_back(final ? 1 : 0);
-        if (!final && (finishing || ((s->dma_issued - s->hash_issued) & ~63ull))) again.push_back(sp);
+        c.job_slabs.push_back(job_slab);
+        if (!final && (finishing || !s->staged.empty() || (!s->verify_only && ((s->dma_issued - s->hash_issued) & ~63ull)))) again.push_back(sp);
         else s->queued = false;
     }
     ready.swap(again);
@@ -796,8 +830,9 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
         std::vector<dm::HashJob> tmp(c.h_jobs, c.h_jobs + c.njobs);
         std::vector<std::shared_ptr<Stream>> st2(c.njobs);
         std::vector<uint8_t> fin2(c.njobs);
-        for (uint32_t i = 0; i < c.njobs; ++i) { c.h_jobs[i] = tmp[order[i]]; st2[i] = c.streams[order[i]]; fin2[i] = c.is_final[order[i]]; }
-        c.streams.swap(st2); c.is_final.swap(fin2);
+        std::vector<Slab *> sl2(c.njobs);
+        for (uint32_t i = 0; i < c.njobs; ++i) { c.h_jobs[i] = tmp[order[i]]; st2[i] = c.streams[order[i]]; fin2[i] = c.is_final[order[i]]; sl2[i] = c.job_slabs[order[i]]; }
+        c.streams.swap(st2); c.is_final.swap(fin2); c.job_slabs.swap(sl2);
     }
     cudaMemcpyAsync(c.d_jobs, c.h_jobs, sizeof(dm::HashJob) * c.njobs, cudaMemcpyHostToDevice, c.stream);
     cudaEventRecord(c.k_start, c.stream);
@@ -987,6 +1022,19 @@ void spill_main(dm_engine *e)
     }
 }
 
+// The device mirror of the ring exists from the start with DM_F_NO_HBM_CAS, otherwise it is
+// allocated the first time a blob too large for the arena shows up.
+int ensure_dev_ring(dm_engine *e)
+{
+    std::lock_guard<std::mutex> g(e->slab_mu);
+    if (e->dev_ring) return DM_OK;
+    cudaSetDevice(e->device);
+    const uint64_t bytes = (uint64_t)e->slab_store.size() * e->cfg.slab_bytes;
+    CU_TRY(cudaMalloc(&e->dev_ring, bytes));
+    for (size_t i = 0; i < e->slab_store.size(); ++i) e->slab_store[i].dev = e->dev_ring + i * e->cfg.slab_bytes;
+    return DM_OK;
+}
+
 std::shared_ptr<Stream> find_stream(dm_engine *e, uint64_t id)
 {
     const int k = (int)(id % kStripes);
@@ -1101,6 +1149,7 @@ void dm_engine_destroy(dm_engine *e)
     if (e->d_states) cudaFree(e->d_states);
     if (e->h_digests) cudaFreeHost(e->h_digests);
     if (e->ring) cudaFreeHost(e->ring);
+    if (e->dev_ring) cudaFree(e->dev_ring);
     if (e->arena_base) cudaFree(e->arena_base);
     for (int i = 0; i < kCopyStreams; ++i) if (e->copy_stream[i]) cudaStreamDestroy(e->copy_stream[i]);
     if (e->ingest_stream) cudaStreamDestroy(e->ingest_stream);
@@ -1120,7 +1169,6 @@ int dm_engine_create(const dm_config *cfg, dm_engine **out)
     }
     if (cfg->device < 0 || cfg->device >= ndev) return fail(DM_ENODEV, "device ordinal out of range");
     if (cfg->slab_bytes && (cfg->slab_bytes % 256)) return fail(DM_EINVAL, "slab_bytes must be a multiple of 256");
-    if (cfg->flags & DM_F_NO_HBM_CAS) return fail(DM_EINVAL, "DM_F_NO_HBM_CAS: use dm_ingest_device(DM_ING_HASH_ONLY)");
 
     dm_engine *e = new dm_engine();
     e->cfg = *cfg;
@@ -1161,6 +1209,7 @@ int dm_engine_create(const dm_config *cfg, dm_engine **out)
     CU_INIT(cudaEventCreate(&e->ing_ev0));
     CU_INIT(cudaEventCreate(&e->ing_ev1));
 
+    if ((e->cfg.flags & DM_F_NO_HBM_CAS) && !e->cfg.hbm_cas_bytes) e->cfg.hbm_cas_bytes = 1u << 20;   // only dm_ingest_device would use it
     if (!e->cfg.hbm_cas_bytes) {
         size_t fr = 0, tot = 0;
         CU_INIT(cudaMemGetInfo(&fr, &tot));
@@ -1173,7 +1222,12 @@ int dm_engine_create(const dm_config *cfg, dm_engine **out)
     const uint64_t nslab = e->cfg.ring_bytes / e->cfg.slab_bytes;
     CU_INIT(cudaHostAlloc(&e->ring, nslab * e->cfg.slab_bytes, cudaHostAllocDefault));
     e->slab_store.resize(nslab);
-    for (uint64_t i = 0; i < nslab; ++i) { e->slab_store[i].host = e->ring + i * e->cfg.slab_bytes; e->slab_free.push_back(&e->slab_store[i]); }
+    if (e->cfg.flags & DM_F_NO_HBM_CAS) CU_INIT(cudaMalloc(&e->dev_ring, nslab * e->cfg.slab_bytes));
+    for (uint64_t i = 0; i < nslab; ++i) {
+        e->slab_store[i].host = e->ring + i * e->cfg.slab_bytes;
+        e->slab_store[i].dev = e->dev_ring ? e->dev_ring + i * e->cfg.slab_bytes : nullptr;
+        e->slab_free.push_back(&e->slab_store[i]);
+    }
 
     CU_INIT(cudaMalloc(&e->d_states, 32ull * e->cfg.max_streams));
     CU_INIT(cudaHostAlloc(&e->h_digests, 32ull * e->cfg.max_streams, cudaHostAllocMapped));
@@ -1236,7 +1290,18 @@ int dm_stream_open(dm_engine *e, const uint8_t expect[32], uint64_t size_hint, u
         e->free_slots.pop_back();
         sp->id = e->next_id++;
     }
-    if (size_hint) {
+    sp->verify_only = (e->cfg.flags & DM_F_NO_HBM_CAS) != 0;
+    if (!sp->verify_only && size_hint > e->cfg.hbm_cas_bytes) {
+        // can never be cached here: still verify it, through the device mirror of the ring
+        int rc = ensure_dev_ring(e);
+        if (rc != DM_OK) {
+            std::lock_guard<std::mutex> g2(e->mu);
+            e->free_slots.push_back(sp->slot);
+            return rc;
+        }
+        sp->verify_only = true;
+    }
+    if (size_hint && !sp->verify_only) {
         cudaSetDevice(e->device);
         std::lock_guard<std::mutex> g(sp->mu);
         Extent x;
@@ -1299,6 +1364,7 @@ int dm_stream_write_at(dm_engine *e, uint64_t id, uint64_t offset, const void *b
         g.unlock();
         return dm_stream_write(e, id, buf, len);          // plain sequential continuation
     }
+    if (s->verify_only) return fail(DM_ESTATE, "out-of-order ranges need the HBM store (engine is verify-only)");
     const uint8_t *p = static_cast<const uint8_t *>(buf);
     const uint32_t slab_bytes = e->cfg.slab_bytes;
     while (len) {
@@ -1351,7 +1417,9 @@ int dm_stream_checkpoint(dm_engine *e, uint64_t id, dm_checkpoint *out)
     Stream *s = sp.get();
     std::unique_lock<std::mutex> g(s->mu);
     if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open");
-    {   // push out what is staged so the checkpoint covers every whole block received in order
+    if (!s->verify_only || (s->cur_fill & 63) == 0) {
+        // push out what is staged so the checkpoint covers every whole block received in order
+        // (a verify-only stream hashes slab by slab, so only a block-aligned partial slab may go early)
         int rc = submit_slab(e, sp);
         if (rc != DM_OK) return rc;
     }
@@ -1492,6 +1560,12 @@ int dm_stream_abort(dm_engine *e, uint64_t id)
         if (s->cur) { slab_put(e, s->cur); s->cur = nullptr; s->cur_fill = 0; }
         for (Stream::Part &pt : s->parts) slab_put(e, pt.slab);
         s->parts.clear();
+        if (!s->staged.empty()) {            // their DMAs may be in flight: drain before the ring reuses them
+            cudaSetDevice(e->device);
+            cudaStreamSynchronize(e->copy_stream[s->id % kCopyStreams]);
+            for (auto &ps : s->staged) slab_put(e, ps.first);
+            s->staged.clear();
+        }
         s->st = St::Aborted;
         free_now = s->jobs_inflight == 0;
     }

@@ -54,7 +54,9 @@ typedef enum dm_err {
 typedef struct dm_engine dm_engine;   /* opaque; owned by caller between create/destroy */
 
 /* dm_config.flags */
-#define DM_F_NO_HBM_CAS   0x1u  /* hash + verify only; bytes are not retained in HBM */
+#define DM_F_NO_HBM_CAS   0x1u  /* verify only: streams are hashed from a device mirror of the ring and
+                                  * nothing is retained or published (also what a blob whose size_hint
+                                  * exceeds hbm_cas_bytes gets automatically) */
 #define DM_F_DISK_SYNC    0x2u  /* dm_stream_finish returns only after the disk tier holds the blob */
 
 typedef struct dm_config {
