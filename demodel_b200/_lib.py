@@ -84,6 +84,7 @@ SIGNATURES = {
     "dm_stream_write_at": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, C.c_size_t]),
     "dm_stream_checkpoint": (C.c_int, [_P, C.c_uint64, C.POINTER(DmCheckpoint)]),
     "dm_stream_resume": (C.c_int, [_P, C.POINTER(DmCheckpoint), _P, C.c_uint64, _U64P]),
+    "dm_stream_set_meta": (C.c_int, [_P, C.c_uint64, C.c_char_p, C.c_char_p]),
     "dm_stream_acquire": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "dm_stream_commit": (C.c_int, [_P, C.c_uint64, C.c_size_t]),
     "dm_stream_flush": (C.c_int, [_P, C.c_uint64]),
@@ -92,6 +93,7 @@ SIGNATURES = {
     "dm_cache_contains": (C.c_int, [_P, _P, _U64P]),
     "dm_cache_open": (C.c_int, [_P, _P, _U64P, _U64P]),
     "dm_cache_read": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "dm_cache_meta": (C.c_int, [_P, C.c_uint64, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dm_cache_close": (C.c_int, [_P, C.c_uint64]),
     "dm_cache_evict": (C.c_int, [_P, _P]),
     "dm_cache_device_extents": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), _U64P, C.c_uint32]),

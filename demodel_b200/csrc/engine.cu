@@ -155,6 +155,7 @@ struct Blob {
     bool in_hbm = false;
     bool on_disk = false;
     bool spill_done = false;
+    std::vector<std::pair<std::string, std::string>> meta;   // response headers to replay on a hit
 };
 
 struct Slab { uint8_t *host; uint8_t *dev; };   // dev: same slab of the device-side mirror (verify-only streams)
@@ -188,6 +189,7 @@ struct Stream {
     // job in arrival order; a slab returns to the ring when its job has run.
     bool verify_only = false;
     std::deque<std::pair<Slab *, uint32_t>> staged;
+    std::vector<std::pair<std::string, std::string>> meta;   // dm_stream_set_meta
     bool window_out = false;   // acquire() window outstanding
     bool queued = false;       // in the pump's inbox / ready list (guarded by mu)
     bool final_issued = false;
@@ -204,6 +206,7 @@ struct Window { Bounce *b = nullptr; uint64_t off = 0, len = 0; bool pending = f
 
 struct Reader {
     std::shared_ptr<Blob> blob;
+    std::string disk_meta;        // sidecar text, disk-tier readers
     int fd = -1;                  // disk tier
     uint64_t size = 0;
     std::mutex mu;                // a reader is normally one goroutine; this keeps misuse safe
@@ -564,12 +567,35 @@ bool range_taken(const Stream *s, uint64_t off, uint64_t len, const Stream::Part
 
 // ---- CAS commit --------------------------------------------------------------
 
+std::string json_quote(const std::string &v)
+{
+    std::string o = "\"";
+    for (unsigned char c : v) {
+        if (c == '"' || c == '\\') { o += '\\'; o += (char)c; }
+        else if (c < 0x20) { char t[8]; snprintf(t, sizeof t, "\\u%04x", c); o += t; }
+        else o += (char)c;
+    }
+    return o + "\"";
+}
+
+// The sidecar: what a hit needs besides the bytes.  The digest is over the
+// identity-encoded body, which is what HF LFS oids and OCI layer digests are defined on.
+std::string sidecar_json(const Blob &b)
+{
+    std::string o = "{\"digest\":\"sha256:" + hex_of(b.digest.b, 32) + "\",\"size\":" + std::to_string(b.size) +
+                    ",\"encoding\":\"identity\",\"engine\":\"demodel_b200\",\"abi\":" + std::to_string(DM_ABI_VERSION) +
+                    ",\"headers\":{";
+    for (size_t i = 0; i < b.meta.size(); ++i)
+        o += (i ? "," : "") + json_quote(b.meta[i].first) + ":" + json_quote(b.meta[i].second);
+    return o + "}}\n";
+}
+
 void write_sidecar(const std::string &path, const Blob &b)
 {
     FILE *f = fopen(path.c_str(), "w");
     if (!f) return;
-    fprintf(f, "{\"digest\":\"sha256:%s\",\"size\":%llu,\"encoding\":\"identity\",\"engine\":\"demodel_b200\",\"abi\":%u}\n",
-            hex_of(b.digest.b, 32).c_str(), (unsigned long long)b.size, DM_ABI_VERSION);
+    const std::string j = sidecar_json(b);
+    fwrite(j.data(), 1, j.size(), f);
     fclose(f);
 }
 
@@ -581,7 +607,8 @@ std::string blob_path(const dm_engine *e, const uint8_t d[32])
 
 // Publish a verified blob.  Returns the blob that now owns the digest (an
 // earlier copy wins; the new extents are then released).
-std::shared_ptr<Blob> publish(dm_engine *e, const Digest &d, uint64_t size, std::vector<Extent> &ext)
+std::shared_ptr<Blob> publish(dm_engine *e, const Digest &d, uint64_t size, std::vector<Extent> &ext,
+                              std::vector<std::pair<std::string, std::string>> *meta = nullptr)
 {
     // trim the last extent to the bytes actually held
     uint64_t keep = round_up(std::max<uint64_t>(size, 1), kAlign), base = 0;
@@ -615,6 +642,7 @@ std::shared_ptr<Blob> publish(dm_engine *e, const Digest &d, uint64_t size, std:
             b = std::make_shared<Blob>();
             b->digest = d; b->size = size; b->extents = kept; kept.clear();
             b->in_hbm = true; b->tick = ++e->tick;
+            if (meta) b->meta.swap(*meta);
             e->blobs[d] = b;
             fresh = true;
         }
@@ -717,7 +745,9 @@ void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint
                         s->prefix_cover.begin()->second >= s->resume_base);
     g.unlock();
     std::shared_ptr<Blob> b;
-    if (matched && whole && !s->verify_only) b = publish(e, d, size, ext);
+    std::vector<std::pair<std::string, std::string>> meta;
+    g.lock(); meta.swap(s->meta); g.unlock();
+    if (matched && whole && !s->verify_only) b = publish(e, d, size, ext, &meta);
     else { free_extents(e, ext); if (!matched) e->st_mismatch++; }
     g.lock();
     s->blob = b;
@@ -1460,6 +1490,19 @@ int dm_stream_resume(dm_engine *e, const dm_checkpoint *ck, const uint8_t expect
     return DM_OK;
 }
 
+int dm_stream_set_meta(dm_engine *e, uint64_t id, const char *key, const char *value)
+{
+    if (!e || !key || !value) return fail(DM_EINVAL, "null argument");
+    auto sp = find_stream(e, id);
+    if (!sp) return fail(DM_EINVAL, "unknown stream id");
+    std::lock_guard<std::mutex> g(sp->mu);
+    if (sp->st != St::Open) return fail(DM_ESTATE, "stream not open");
+    if (sp->meta.size() >= 64) return fail(DM_ENOMEM, "too many metadata entries");
+    for (auto &kv : sp->meta) if (kv.first == key) { kv.second = value; return DM_OK; }
+    sp->meta.emplace_back(key, value);
+    return DM_OK;
+}
+
 int dm_stream_acquire(dm_engine *e, uint64_t id, void **ptr, size_t *cap)
 {
     if (!e || !ptr || !cap) return fail(DM_EINVAL, "null argument");
@@ -1627,6 +1670,12 @@ int dm_cache_open(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint
         struct stat st;
         fstat(r->fd, &st);
         r->size = (uint64_t)st.st_size;
+        if (FILE *mf = fopen((blob_path(e, digest) + ".meta").c_str(), "r")) {
+            char tmp[4096];
+            size_t k;
+            while ((k = fread(tmp, 1, sizeof tmp, mf)) > 0) r->disk_meta.append(tmp, k);
+            fclose(mf);
+        }
     }
     uint64_t id;
     {
@@ -1751,6 +1800,25 @@ int dm_cache_read(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t
     e->st_served += done;
     if (nread) *nread = done;
     return rc;
+}
+
+int dm_cache_meta(dm_engine *e, uint64_t reader, char *buf, size_t cap, size_t *len)
+{
+    if (!e || !len || (!buf && cap)) return fail(DM_EINVAL, "null argument");
+    std::shared_ptr<Reader> r = find_reader(e, reader);
+    if (!r) return fail(DM_EINVAL, "unknown reader id");
+    std::string j;
+    if (r->blob) {
+        std::lock_guard<std::mutex> g(e->mu);
+        j = sidecar_json(*r->blob);
+    } else j = r->disk_meta;
+    *len = j.size();
+    if (cap) {
+        const size_t n = std::min(cap - 1, j.size());
+        memcpy(buf, j.data(), n);
+        buf[n] = 0;
+    }
+    return DM_OK;
 }
 
 int dm_cache_close(dm_engine *e, uint64_t reader)

@@ -113,6 +113,9 @@ class Engine:
               "dm_stream_resume")
         return sid.value
 
+    def stream_set_meta(self, sid: int, key: str, value: str) -> None:
+        check(self._lib.dm_stream_set_meta(self._h, sid, key.encode(), value.encode()), "dm_stream_set_meta")
+
     def stream_acquire(self, sid: int) -> tuple[int, int]:
         ptr, cap = C.c_void_p(), C.c_size_t()
         check(self._lib.dm_stream_acquire(self._h, sid, C.byref(ptr), C.byref(cap)), "dm_stream_acquire")
@@ -169,6 +172,15 @@ class Engine:
         got = C.c_size_t()
         check(self._lib.dm_cache_read(self._h, rid, off, C.c_void_p(out.ctypes.data), n, C.byref(got)), "dm_cache_read")
         return out[:got.value].tobytes()
+
+    def cache_meta(self, rid: int) -> dict:
+        """The blob's sidecar (digest, size, encoding, replayable response headers)."""
+        import json
+        n = C.c_size_t()
+        check(self._lib.dm_cache_meta(self._h, rid, None, 0, C.byref(n)), "dm_cache_meta")
+        buf = C.create_string_buffer(n.value + 1)
+        check(self._lib.dm_cache_meta(self._h, rid, buf, n.value + 1, C.byref(n)), "dm_cache_meta")
+        return json.loads(buf.value.decode())
 
     def cache_close(self, rid: int) -> None:
         check(self._lib.dm_cache_close(self._h, rid), "dm_cache_close")

@@ -348,3 +348,25 @@ func ParseManifest(body []byte) ([]Layer, error) {
 	}
 	return out, nil
 }
+
+// SetMeta records a response header to replay when the blob is served from
+// the cache (stored in the sidecar on the disk tier).
+func (t *BodyTee) SetMeta(key, value string) error {
+	k, v := C.CString(key), C.CString(value)
+	defer C.free(unsafe.Pointer(k))
+	defer C.free(unsafe.Pointer(v))
+	return check(C.dm_stream_set_meta(t.e, t.id, k, v))
+}
+
+// Meta returns the blob's sidecar JSON ({"digest","size","encoding","headers":{...}}).
+func (r *HitReader) Meta() (string, error) {
+	var n C.size_t
+	if err := check(C.dm_cache_meta(r.e, r.id, nil, 0, &n)); err != nil {
+		return "", err
+	}
+	buf := make([]byte, int(n)+1)
+	if err := check(C.dm_cache_meta(r.e, r.id, (*C.char)(unsafe.Pointer(&buf[0])), C.size_t(len(buf)), &n)); err != nil {
+		return "", err
+	}
+	return string(buf[:int(n)]), nil
+}

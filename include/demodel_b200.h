@@ -133,6 +133,11 @@ typedef struct dm_checkpoint {
 int dm_stream_checkpoint(dm_engine *e, uint64_t id, dm_checkpoint *out);
 int dm_stream_resume(dm_engine *e, const dm_checkpoint *ck, const uint8_t expect[32], uint64_t size_hint, uint64_t *id);
 
+/* Response headers worth replaying on a hit (Content-Type, ETag, Last-Modified,
+ * the request URL ...).  Stored with the blob — in the `.meta` sidecar on the
+ * disk tier — and returned by dm_cache_meta.  At most 64 entries per stream. */
+int dm_stream_set_meta(dm_engine *e, uint64_t id, const char *key, const char *value);
+
 /* Zero-copy variant: borrow a window of the pinned ring, Read() into it,
  * then commit the bytes actually read.  At most one outstanding window per
  * stream; *cap >= 1 on success. */
@@ -154,6 +159,9 @@ int dm_stream_abort(dm_engine *e, uint64_t id);
 int dm_cache_contains(dm_engine *e, const uint8_t digest[32], uint64_t *size);  /* DM_ENOENT on miss */
 int dm_cache_open(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size);
 int dm_cache_read(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t len, size_t *nread);
+/* The blob's sidecar as JSON text: {"digest":"sha256:..","size":N,"encoding":"identity",
+ * ..,"headers":{..}}.  *len receives the full length; up to cap-1 bytes + NUL are copied. */
+int dm_cache_meta(dm_engine *e, uint64_t reader, char *buf, size_t cap, size_t *len);
 int dm_cache_close(dm_engine *e, uint64_t reader);
 int dm_cache_evict(dm_engine *e, const uint8_t digest[32]);   /* HBM tier only; disk copy stays */
 
