@@ -21,6 +21,7 @@
 #include "../../include/demodel_b200.h"
 #include "sha256_kernels.cuh"
 #include "blobgen.h"
+#include "host_util.hpp"
 
 #include <cuda_runtime.h>
 
@@ -47,6 +48,9 @@
 #include <unistd.h>
 
 namespace {
+
+using dm::Arena;
+using dm::add_interval;
 
 thread_local std::string g_last_error;
 
@@ -108,43 +112,6 @@ std::string hex_of(const uint8_t *d, size_t n)
 }
 
 struct Extent { uint64_t off, len; };      // byte range of the HBM arena
-
-// First-fit free list over the HBM arena, coalescing on free.
-class Arena {
-public:
-    void reset(uint64_t bytes) { free_.clear(); if (bytes) free_[0] = bytes; cap_ = bytes; used_ = 0; }
-    bool alloc(uint64_t len, uint64_t *off)
-    {
-        for (auto it = free_.begin(); it != free_.end(); ++it) {
-            if (it->second >= len) {
-                *off = it->first;
-                const uint64_t rest = it->second - len, at = it->first + len;
-                free_.erase(it);
-                if (rest) free_[at] = rest;
-                used_ += len;
-                return true;
-            }
-        }
-        return false;
-    }
-    void release(uint64_t off, uint64_t len)
-    {
-        if (!len) return;
-        used_ -= len;
-        auto nx = free_.lower_bound(off);
-        if (nx != free_.begin()) {
-            auto pv = std::prev(nx);
-            if (pv->first + pv->second == off) { off = pv->first; len += pv->second; free_.erase(pv); }
-        }
-        if (nx != free_.end() && off + len == nx->first) { len += nx->second; free_.erase(nx); }
-        free_[off] = len;
-    }
-    uint64_t used() const { return used_; }
-    uint64_t capacity() const { return cap_; }
-private:
-    std::map<uint64_t, uint64_t> free_;
-    uint64_t cap_ = 0, used_ = 0;
-};
 
 struct Blob {
     Digest digest;
@@ -483,15 +450,6 @@ int dma_range(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *slab, uint6
     if (err != cudaSuccess) { slab_put(e, slab); return fail_cuda(err, "cudaMemcpyAsync(H2D slab)"); }
     e->st_h2d += n;
     return DM_OK;
-}
-
-void add_interval(std::map<uint64_t, uint64_t> &m, uint64_t lo, uint64_t hi)
-{
-    if (lo >= hi) return;
-    auto it = m.lower_bound(lo);
-    if (it != m.begin()) { auto pv = std::prev(it); if (pv->second >= lo) { lo = pv->first; hi = std::max(hi, pv->second); it = m.erase(pv); } }
-    while (it != m.end() && it->first <= hi) { hi = std::max(hi, it->second); it = m.erase(it); }
-    m[lo] = hi;
 }
 
 // The contiguous frontier swallows islands that now touch it.  Stream mutex held.
