@@ -69,6 +69,15 @@ def _cpu_quota():
         return None
 
 
+def _kernel_for(n):
+    """Mirror of streams_per_warp_for() in demodel_b200/csrc/sha256_kernels.cuh (for the report only)."""
+    for limit, name in ((640, "deep (1 stream/warp)"), (3072, "group (4 streams/warp)"), (6144, "group (8 streams/warp)"),
+                        (12288, "group (16 streams/warp)")):
+        if n <= limit:
+            return name
+    return "wide (32 streams/warp)"
+
+
 def _layout(sizes):
     offs, pos = [], 0
     for s in sizes:
@@ -462,7 +471,7 @@ def main():
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": args.workload, "baseline_config": WORKLOADS[args.workload]["baseline_config"],
                        "blobs_per_gpu": n, "bytes_per_gpu_per_step": total, "mode": "hash-only" if args.hash_only else "hash-and-cache (fused CAS copy)",
-                       "kernel": args.kernel or ("deep" if n < 1024 else "wide"), "seed": hex(SEED),
+                       "kernel": args.kernel or _kernel_for(n), "seed": hex(SEED),
                        "l2": "inputs (%.1f GB) larger than L2 (126 MB); no flush needed" % (total / 1e9),
                        "parallelism": f"shard{world} (URL-hash homed, no collective)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

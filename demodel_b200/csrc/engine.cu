@@ -78,7 +78,8 @@ constexpr int kStripes = 64;               // stream-table lock stripes
 constexpr int kCopyStreams = 2;
 constexpr size_t kBounceBytes = 4u << 20;
 constexpr int kBounces = 48;               // 4 MiB each; readers borrow two as read-ahead windows
-constexpr int kBounceReserve = 4;          // never lent to windows: the spill thread and one-shot reads need some
+constexpr int kSpillThreads = 4;           // disk-tier writers (each double-buffers two bounce buffers)
+constexpr int kBounceReserve = 2 * kSpillThreads + 2;          // never lent to windows: the spill thread and one-shot reads need some
 
 inline uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
@@ -256,7 +257,7 @@ struct dm_engine {
     std::mutex spill_mu;
     std::condition_variable spill_cv, spill_done_cv;
     std::deque<std::shared_ptr<Blob>> spill_q;
-    std::thread spiller;
+    std::vector<std::thread> spillers;   // kSpillThreads writers of the disk tier
 
     std::mutex bounce_mu;
     std::condition_variable bounce_cv;
@@ -612,7 +613,7 @@ std::shared_ptr<Blob> publish(dm_engine *e, const Digest &d, uint64_t size, std:
             std::lock_guard<std::mutex> g(e->spill_mu);
             e->spill_q.push_back(b);
         }
-        e->spill_cv.notify_one();
+        e->spill_cv.notify_all();
     }
     return b;
 }
@@ -655,7 +656,7 @@ void publish_many(dm_engine *e, const std::vector<Verified> &items)
             std::lock_guard<std::mutex> g(e->spill_mu);
             for (auto &b : to_spill) e->spill_q.push_back(b);
         }
-        e->spill_cv.notify_one();
+        e->spill_cv.notify_all();
     }
 }
 
@@ -948,29 +949,42 @@ bool spill_one(dm_engine *e, Blob *b)
     mkdirs(path);
     int fd = open(tmp.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
     if (fd < 0) return false;
-    Bounce *bn = bounce_get(e);
+    // two pinned buffers: the D2H of piece k+1 runs while piece k is written to the file
+    Bounce *bn[2] = {bounce_get(e), bounce_get(e)};
+    uint64_t piece_len[2] = {0, 0};
     bool ok = true;
-    uint64_t off = 0;
-    while (ok && off < b->size) {
+    auto start_piece = [&](int slot, uint64_t off) {
         const uint64_t n = std::min<uint64_t>(kBounceBytes, b->size - off);
-        uint8_t *dst = bn->host;
+        uint8_t *dst = bn[slot]->host;
         cudaError_t err = cudaSuccess;
         for_segments(e, b->extents, off, n, [&](uint8_t *dev, uint64_t len) {
-            if (err == cudaSuccess) err = cudaMemcpyAsync(dst, dev, len, cudaMemcpyDeviceToHost, bn->stream);
+            if (err == cudaSuccess) err = cudaMemcpyAsync(dst, dev, len, cudaMemcpyDeviceToHost, bn[slot]->stream);
             dst += len;
         });
-        if (err == cudaSuccess) err = cudaStreamSynchronize(bn->stream);
-        if (err != cudaSuccess) { ok = false; break; }
+        piece_len[slot] = n;
+        return err == cudaSuccess;
+    };
+    uint64_t issued = 0, written = 0;
+    int cur = 0;
+    if (b->size) { ok = start_piece(0, 0); issued = piece_len[0]; }
+    while (ok && written < b->size) {
+        if (issued < b->size) { ok = start_piece(cur ^ 1, issued); issued += piece_len[cur ^ 1]; }
+        if (cudaStreamSynchronize(bn[cur]->stream) != cudaSuccess) { ok = false; break; }
+        const uint64_t n = piece_len[cur];
         e->st_d2h += n;
         uint64_t w = 0;
         while (w < n) {
-            ssize_t r = write(fd, bn->host + w, n - w);
+            ssize_t r = write(fd, bn[cur]->host + w, n - w);
             if (r < 0) { if (errno == EINTR) continue; ok = false; break; }
             w += (uint64_t)r;
         }
-        off += n;
+        written += n;
+        cur ^= 1;
     }
-    bounce_put(e, bn);
+    cudaStreamSynchronize(bn[0]->stream);
+    cudaStreamSynchronize(bn[1]->stream);
+    bounce_put(e, bn[0]);
+    bounce_put(e, bn[1]);
     close(fd);
     if (ok) ok = rename(tmp.c_str(), path.c_str()) == 0;
     if (ok) write_sidecar(path + ".meta", *b);
@@ -1116,7 +1130,7 @@ void dm_engine_destroy(dm_engine *e)
         std::lock_guard<std::mutex> g(e->spill_mu);
     }
     e->spill_cv.notify_all();
-    if (e->spiller.joinable()) e->spiller.join();
+    for (auto &t : e->spillers) if (t.joinable()) t.join();
     cudaDeviceSynchronize();
     for (auto &m : e->readers) for (auto &kv : m) if (kv.second->fd >= 0) close(kv.second->fd);
     for (Cycle &c : e->cycles) {
@@ -1243,7 +1257,8 @@ int dm_engine_create(const dm_config *cfg, dm_engine **out)
 #undef CU_INIT
     if (!e->cas_dir.empty()) mkdirs(e->cas_dir + "/blobs/sha256/x");
     e->pump = std::thread(pump_main, e);
-    if (!e->cas_dir.empty()) e->spiller = std::thread(spill_main, e);
+    if (!e->cas_dir.empty())
+        for (int i = 0; i < kSpillThreads; ++i) e->spillers.emplace_back(spill_main, e);
     *out = e;
     return DM_OK;
 }
