@@ -55,6 +55,10 @@ class DmStats(C.Structure):
         ("open_streams", C.c_uint64),
         ("ring_waits", C.c_uint64),
         ("launches_group", C.c_uint64),
+        ("ring_slabs_total", C.c_uint64),
+        ("ring_slabs_free", C.c_uint64),
+        ("open_readers", C.c_uint64),
+        ("free_stream_slots", C.c_uint64),
     ]
 
 

@@ -237,6 +237,7 @@ struct dm_engine {
     std::mutex stripe_mu[kStripes];  // stream table, striped by id: dm_stream_write never takes `mu`
     std::unordered_map<uint64_t, std::shared_ptr<Stream>> streams[kStripes];
     std::atomic<uint64_t> n_streams{0};
+    std::atomic<bool> ring_starved{false};
     std::vector<uint32_t> free_slots;
     uint64_t next_id = 1;
     std::unordered_map<Digest, std::shared_ptr<Blob>, DigestHash> blobs;
@@ -387,7 +388,14 @@ int ensure_capacity(dm_engine *e, Stream *s, uint64_t need)
 Slab *slab_get(dm_engine *e)
 {
     std::unique_lock<std::mutex> g(e->slab_mu);
-    if (e->slab_free.empty() && !e->stop) e->st_ring_waits++;
+    if (e->slab_free.empty() && !e->stop) {
+        e->st_ring_waits++;
+        // Every slab is out: some are only partly filled and held by streams waiting for their next
+        // bytes.  Ask the pump to DMA those early so they recycle (otherwise more live streams than
+        // slabs would starve — or, with one thread driving many streams, deadlock).
+        { std::lock_guard<std::mutex> gw(e->work_mu); e->ring_starved.store(true); }   // under the pump's mutex: no lost wake-up
+        e->work_cv.notify_one();
+    }
     e->slab_cv.wait(g, [&] { return !e->slab_free.empty() || e->stop; });
     if (e->slab_free.empty()) return nullptr;
     Slab *s = e->slab_free.back();
@@ -834,6 +842,24 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
     return true;
 }
 
+// Ring back-pressure relief (pump thread): DMA the partly filled sequential slabs of open streams so
+// they return to the ring.  try_lock only — a stream busy in a write keeps its slab this round.
+void flush_partial_slabs(dm_engine *e)
+{
+    std::vector<std::shared_ptr<Stream>> all;
+    for (int k = 0; k < kStripes; ++k) {
+        std::lock_guard<std::mutex> g(e->stripe_mu[k]);
+        for (auto &kv : e->streams[k]) all.push_back(kv.second);
+    }
+    for (auto &sp : all) {
+        Stream *s = sp.get();
+        std::unique_lock<std::mutex> g(s->mu, std::try_to_lock);
+        if (!g.owns_lock() || s->st != St::Open || s->window_out || !s->cur || s->cur_fill == 0) continue;
+        if (s->verify_only && (s->cur_fill & 63)) continue;      // slab-by-slab hashing needs whole blocks
+        submit_slab(e, sp);
+    }
+}
+
 // The pump owns all launch decisions.  Policy: at most one JOB PER STREAM in
 // flight (its next job chains on the state the running one writes), but up to
 // kCycles LAUNCHES in flight, each on its own CUDA stream.  A launch costs its
@@ -861,6 +887,7 @@ void pump_main(dm_engine *e)
             b.slabs.clear(); b.busy = false;
             b_tail = (b_tail + 1) % kSlabBatches; --b_live;
         }
+        if (e->ring_starved.exchange(false)) flush_partial_slabs(e);
         // 2. finished hash launches (any order)
         bool reaped = false;
         for (Cycle &c : e->cycles)
@@ -871,7 +898,7 @@ void pump_main(dm_engine *e)
             std::unique_lock<std::mutex> g(e->work_mu);
             const bool idle = !n_inflight && !b_live && ready.empty() && slabs.empty();
             if (e->dirty.empty() && e->pending_slabs.empty() && !e->stop && !launched && !reaped) {
-                if (idle) e->work_cv.wait(g, [&] { return !e->dirty.empty() || !e->pending_slabs.empty() || e->stop; });
+                if (idle) e->work_cv.wait(g, [&] { return !e->dirty.empty() || !e->pending_slabs.empty() || e->stop || e->ring_starved.load(); });
                 else e->work_cv.wait_for(g, std::chrono::microseconds(40));
             }
             stopping = e->stop;
@@ -1276,6 +1303,9 @@ int dm_engine_stats(dm_engine *e, dm_stats *o)
     o->open_streams = e->n_streams;
     o->ring_waits = e->st_ring_waits;
     o->launches_group = e->st_group;
+    { std::lock_guard<std::mutex> g(e->slab_mu); o->ring_slabs_total = e->slab_store.size(); o->ring_slabs_free = e->slab_free.size(); }
+    for (int k = 0; k < kStripes; ++k) { std::lock_guard<std::mutex> g(e->reader_mu[k]); o->open_readers += e->readers[k].size(); }
+    { std::lock_guard<std::mutex> g(e->mu); o->free_stream_slots = e->free_slots.size(); }
     return DM_OK;
 }
 

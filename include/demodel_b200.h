@@ -88,6 +88,10 @@ typedef struct dm_stats {
     uint64_t open_streams;
     uint64_t ring_waits;          /* times a writer had to wait for a free ring slab (back-pressure) */
     uint64_t launches_group;      /* launches of the S-streams-per-warp kernel (counted in kernel_launches) */
+    uint64_t ring_slabs_total;    /* leak accounting: every slab is either free, being filled, or in flight */
+    uint64_t ring_slabs_free;
+    uint64_t open_readers;
+    uint64_t free_stream_slots;   /* == max_streams when no stream is open or draining */
 } dm_stats;
 
 /* ---- engine lifetime (start.go:167-216) -------------------------------- */
