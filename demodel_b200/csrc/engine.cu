@@ -328,6 +328,7 @@ bool evict_for(dm_engine *e, uint64_t need)
 {
     for (;;) {
         std::shared_ptr<Blob> victim;
+        std::vector<Extent> ext;
         {
             std::lock_guard<std::mutex> g(e->mu);
             for (auto &kv : e->blobs) {
@@ -338,28 +339,26 @@ bool evict_for(dm_engine *e, uint64_t need)
             }
             if (!victim) return false;
             victim->in_hbm = false;
+            ext.swap(victim->extents);          // taken under the lock: a re-publish may install new ones at once
             if (!victim->on_disk) e->blobs.erase(victim->digest);
         }
-        uint64_t freed = 0;
-        for (const Extent &x : victim->extents) freed += x.len;
-        free_extents(e, victim->extents);
+        free_extents(e, ext);
         std::lock_guard<std::mutex> g(e->arena_mu);
         uint64_t off;
         if (e->arena.alloc(need, &off)) { e->arena.release(off, need); return true; }
-        (void)freed;
     }
 }
 
 bool arena_alloc(dm_engine *e, uint64_t len, Extent *out)
 {
     len = round_up(std::max<uint64_t>(len, 1), kAlign);
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 4; ++attempt) {      // another thread may take what an eviction freed
         {
             std::lock_guard<std::mutex> g(e->arena_mu);
             uint64_t off;
             if (e->arena.alloc(len, &off)) { out->off = off; out->len = len; return true; }
         }
-        if (attempt == 0 && !evict_for(e, len)) return false;
+        if (!evict_for(e, len)) return false;
     }
     return false;
 }
@@ -671,7 +670,7 @@ void publish_many(dm_engine *e, const std::vector<Verified> &items)
 // Batch eviction (DM_ING_REPLACE): drop the HBM copies of these digests under one lock each way.
 void evict_many(dm_engine *e, const uint8_t *digests, uint32_t n)
 {
-    std::vector<std::shared_ptr<Blob>> victims;
+    std::vector<Extent> ext;
     {
         std::lock_guard<std::mutex> g(e->mu);
         for (uint32_t i = 0; i < n; ++i) {
@@ -680,15 +679,12 @@ void evict_many(dm_engine *e, const uint8_t *digests, uint32_t n)
             auto it = e->blobs.find(d);
             if (it == e->blobs.end() || !it->second->in_hbm || it->second->readers) continue;
             it->second->in_hbm = false;
-            victims.push_back(it->second);
+            ext.insert(ext.end(), it->second->extents.begin(), it->second->extents.end());
+            it->second->extents.clear();            // under the lock (see evict_for)
             if (!it->second->on_disk) e->blobs.erase(it);
         }
     }
-    std::lock_guard<std::mutex> g(e->arena_mu);
-    for (auto &b : victims) {
-        for (const Extent &x : b->extents) e->arena.release(x.off, x.len);
-        b->extents.clear();
-    }
+    free_extents(e, ext);
 }
 
 // ---- pump ----------------------------------------------------------------------
@@ -745,6 +741,8 @@ void reap_cycle(dm_engine *e, Cycle &c)
         }
         if (wake) sp->cv.notify_all();
         if (free_now) {
+            // slabs written after this job was built may still be landing in the extent (see dm_stream_abort)
+            cudaStreamSynchronize(e->copy_stream[sp->id % kCopyStreams]);
             free_extents(e, sp->extents);
             std::lock_guard<std::mutex> g(e->mu);
             e->free_slots.push_back(sp->slot);
@@ -1858,6 +1856,7 @@ int dm_cache_evict(dm_engine *e, const uint8_t digest[32])
     Digest d;
     memcpy(d.b, digest, 32);
     std::shared_ptr<Blob> b;
+    std::vector<Extent> ext;
     {
         std::lock_guard<std::mutex> g(e->mu);
         auto it = e->blobs.find(d);
@@ -1865,9 +1864,10 @@ int dm_cache_evict(dm_engine *e, const uint8_t digest[32])
         if (it->second->readers) return fail(DM_ESTATE, "blob has open readers");
         b = it->second;
         b->in_hbm = false;
+        ext.swap(b->extents);                       // under the lock (see evict_for)
         if (!b->on_disk) e->blobs.erase(it);
     }
-    free_extents(e, b->extents);
+    free_extents(e, ext);
     return DM_OK;
 }
 
