@@ -814,7 +814,11 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
         cudaEventRecord(c.copy_ev[i], e->copy_stream[i]);
         cudaStreamWaitEvent(c.stream, c.copy_ev[i], 0);
     }
-    const int spw = e->force_spw ? e->force_spw : dm::streams_per_warp_for(c.njobs);
+    // Launches overlap on the GPU, so what decides the kernel shape is how many jobs will be
+    // co-resident (this launch + those still running), not the size of this launch alone.
+    uint32_t resident = c.njobs;
+    for (const Cycle &o : e->cycles) if (o.busy) resident += o.njobs;
+    const int spw = e->force_spw ? e->force_spw : dm::streams_per_warp_for(resident);
     c.deep = spw == 1;
     if (spw > 1) {
         // lanes of a warp run in lock step: keep neighbours the same length
