@@ -64,7 +64,7 @@ extern "C" int dm_proxy_drive(dm_engine *e, const void *host_base, const uint64_
     };
 
     auto worker = [&](uint32_t share) {
-        std::vector<uint8_t> buf(zero_copy ? 0 : chunk);       // goproxy's copy buffer
+        std::vector<uint8_t> buf(chunk);                       // goproxy's copy buffer
         std::vector<std::unique_ptr<Conn>> live, draining;
         auto note_err = [&](int rc) { int exp = DM_OK; first_err.compare_exchange_strong(exp, rc); };
         auto open_next = [&]() -> bool {
@@ -82,9 +82,33 @@ extern "C" int dm_proxy_drive(dm_engine *e, const void *host_base, const uint64_
         bool more = true;
         while (more && live.size() < share) more = open_next();
         while (!live.empty()) {
+            if (zero_copy >= 2) {
+                // io.ReadCloser exactly as goproxy drives it: this thread IS the goroutine of one
+                // connection and blocks in Read() at EOF (modes 2/3), or the client goes away half
+                // way and Close() aborts the stream (mode 4).
+                Conn &c = *live.back();
+                const uint64_t len = offsets[c.blob + 1] - offsets[c.blob];
+                uint64_t seen = 0;
+                long got = 1;
+                const void *view = nullptr;
+                while (got > 0) {
+                    if (zero_copy == 4 && seen >= len / 2) { c.tee.Close(); break; }
+                    got = zero_copy == 3 ? c.tee.ReadInPlace(&view, chunk) : c.tee.Read(buf.data(), chunk);
+                    if (got > 0) seen += (uint64_t)got;
+                }
+                if (got < 0) note_err((int)got);
+                else if (zero_copy == 4) { if (matched_out) matched_out[c.blob] = 2; }      // 2 = aborted by the client
+                else {
+                    if (digests_out) memcpy(digests_out + 32ull * c.blob, c.tee.digest(), 32);
+                    if (matched_out) matched_out[c.blob] = c.tee.matched() ? 1 : 0;
+                }
+                live.pop_back();
+                if (more) more = open_next();
+                continue;
+            }
             for (size_t k = 0; k < live.size();) {             // one piece per connection per turn
                 Conn &c = *live[k];
-                const long got = c.tee.Pump(buf.data(), chunk, zero_copy != 0);
+                const long got = c.tee.Pump(buf.data(), chunk, zero_copy == 1);
                 if (got > 0) { ++k; continue; }
                 if (got < 0) note_err((int)got); else draining.push_back(std::move(live[k]));
                 live[k] = std::move(live.back());

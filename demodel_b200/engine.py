@@ -274,10 +274,11 @@ class Engine:
         secs = C.c_double()
         exp = C.cast(C.c_char_p(bytes(expect)), C.c_void_p) if expect is not None else None
         check(self._lib.dm_proxy_drive(self._h, C.c_void_p(host.ctypes.data), off.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                       n, exp, chunk, concurrency, nthreads, 1 if zero_copy else 0,
+                                       n, exp, chunk, concurrency, nthreads, int(zero_copy),
                                        C.c_void_p(dig.ctypes.data), C.c_void_p(mat.ctypes.data), C.byref(secs)),
               "dm_proxy_drive")
-        return [dig[32 * i:32 * i + 32].tobytes() for i in range(n)], [bool(x) for x in mat[:n]], secs.value
+        self.last_drive_verdicts = [int(x) for x in mat[:n]]      # 0 mismatch, 1 matched, 2 aborted by the client
+        return [dig[32 * i:32 * i + 32].tobytes() for i in range(n)], [x == 1 for x in mat[:n]], secs.value
 
     def proxy_serve(self, digests: Iterable[bytes], host_out: np.ndarray, offsets: Sequence[int],
                     chunk: int = 32768, nthreads: int = 1) -> float:

@@ -230,8 +230,11 @@ int  dm_synth_fill_device_many(dm_engine *e, uint64_t seed, uint64_t first_blob,
  * `nthreads` connection workers each pull whole blobs from a shared queue,
  * read them in `chunk`-byte pieces from caller-owned HOST memory
  * [host_base + offsets[i], host_base + offsets[i+1]) and push them through
- * dm_stream_open/write/finish (zero_copy != 0: acquire/commit with the
- * "socket read" landing directly in the ring).  Streams are interleaved
+ * dm_stream_open/write/finish.  zero_copy selects how: 0 copy + non-blocking
+ * EOF (flush), 1 acquire/commit with the "socket read" landing directly in the
+ * ring, 2 / 3 the blocking io.ReadCloser forms of 0 / 1 (one body per thread at
+ * a time), 4 as 2 but the client disconnects half way (Close before EOF:
+ * matched_out[i] = 2, nothing is published).  Streams are interleaved
  * `concurrency` at a time the way concurrent goroutines would be.
  * Returns wall seconds in *seconds. */
 int dm_proxy_drive(dm_engine *e, const void *host_base, const uint64_t *offsets, uint32_t n,
