@@ -100,6 +100,7 @@ SIGNATURES = {
     "dm_cache_meta": (C.c_int, [_P, C.c_uint64, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dm_cache_close": (C.c_int, [_P, C.c_uint64]),
     "dm_cache_evict": (C.c_int, [_P, _P]),
+    "dm_cache_follow": (C.c_int, [_P, _P, _U64P, _U64P]),
     "dm_cache_device_extents": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), _U64P, C.c_uint32]),
     "dm_ingest_device": (C.c_int, [_P, _P, _U64P, _U64P, C.c_uint32, _P, _P, _P, C.c_uint32, C.POINTER(C.c_double)]),
     "dm_manifest_parse": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(DmLayer), C.c_uint32, C.POINTER(C.c_uint32)]),

@@ -158,6 +158,8 @@ struct Stream {
     bool verify_only = false;
     std::deque<std::pair<Slab *, uint32_t>> staged;
     std::vector<std::pair<std::string, std::string>> meta;   // dm_stream_set_meta
+    uint32_t followers = 0;    // readers attached while the body is still arriving (request coalescing)
+    uint64_t size_hint = 0;
     bool window_out = false;   // acquire() window outstanding
     bool queued = false;       // in the pump's inbox / ready list (guarded by mu)
     bool final_issued = false;
@@ -175,6 +177,7 @@ struct Window { Bounce *b = nullptr; uint64_t off = 0, len = 0; bool pending = f
 struct Reader {
     std::shared_ptr<Blob> blob;
     std::string disk_meta;        // sidecar text, disk-tier readers
+    std::shared_ptr<Stream> follow;   // in-flight body this reader is coalesced onto (until it completes)
     int fd = -1;                  // disk tier
     uint64_t size = 0;
     std::mutex mu;                // a reader is normally one goroutine; this keeps misuse safe
@@ -241,6 +244,7 @@ struct dm_engine {
     std::vector<uint32_t> free_slots;
     uint64_t next_id = 1;
     std::unordered_map<Digest, std::shared_ptr<Blob>, DigestHash> blobs;
+    std::unordered_map<Digest, std::weak_ptr<Stream>, DigestHash> inflight;   // open streams by expected digest
     std::mutex reader_mu[kStripes];
     std::unordered_map<uint64_t, std::shared_ptr<Reader>> readers[kStripes];
     uint64_t tick = 0;
@@ -495,6 +499,7 @@ int submit_slab(dm_engine *e, const std::shared_ptr<Stream> &sp)
     s->dma_issued += n;
     absorb_islands(s);
     mark_dirty(e, sp, slab);
+    if (s->followers) s->cv.notify_all();
     return DM_OK;
 }
 
@@ -511,6 +516,7 @@ int submit_part(dm_engine *e, const std::shared_ptr<Stream> &sp, size_t idx)
     else add_interval(s->islands, pt.base, pt.base + pt.fill);
     absorb_islands(s);
     mark_dirty(e, sp, pt.slab);
+    if (s->followers) s->cv.notify_all();
     return DM_OK;
 }
 
@@ -1081,9 +1087,13 @@ void drop_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, bool release_s
         std::lock_guard<std::mutex> g(e->stripe_mu[k]);
         if (e->streams[k].erase(sp->id)) e->n_streams--;
     }
-    if (release_slot) {
+    {
         std::lock_guard<std::mutex> g(e->mu);
-        e->free_slots.push_back(sp->slot);
+        if (release_slot) e->free_slots.push_back(sp->slot);
+        if (sp->has_expect) {
+            auto it = e->inflight.find(sp->expect);
+            if (it != e->inflight.end() && (it->second.expired() || it->second.lock() == sp)) e->inflight.erase(it);
+        }
     }
 }
 
@@ -1348,11 +1358,17 @@ int dm_stream_open(dm_engine *e, const uint8_t expect[32], uint64_t size_hint, u
         sp->extents.push_back(x);
         sp->capacity = x.len;
     }
+    sp->size_hint = size_hint;
     {
         const int k = (int)(sp->id % kStripes);
         std::lock_guard<std::mutex> g(e->stripe_mu[k]);
         e->streams[k][sp->id] = sp;
         e->n_streams++;
+    }
+    if (sp->has_expect && !sp->verify_only) {          // first opener wins; later duplicates are not followable
+        std::lock_guard<std::mutex> g(e->mu);
+        auto &slot = e->inflight[sp->expect];
+        if (slot.expired()) slot = sp;
     }
     *id = sp->id;
     return DM_OK;
@@ -1703,6 +1719,66 @@ static std::shared_ptr<Reader> find_reader(dm_engine *e, uint64_t id)
     return it == e->readers[id % kStripes].end() ? nullptr : it->second;
 }
 
+// Read from a body that is still arriving (request coalescing).  Blocks until bytes past `off` have
+// been DMA'd, the body completes, or it fails.  Returns DM_OK with *nread set, a dm_err, or 1 when the
+// body has completed and been published (the reader has been switched to the blob; caller continues).
+static int follow_read(dm_engine *e, Reader *r, uint64_t off, void *buf, size_t len, size_t *nread)
+{
+    std::lock_guard<std::mutex> gr(r->mu);
+    if (!r->follow) return 1;
+    Stream *s = r->follow.get();
+    std::vector<std::pair<uint8_t *, uint64_t>> segs;
+    size_t n = 0;
+    {
+        std::unique_lock<std::mutex> g(s->mu);
+        s->followers++;
+        s->cv.wait(g, [&] { return s->st == St::Done || s->st == St::Aborted || off < s->dma_issued || len == 0; });
+        s->followers--;
+        if (s->st == St::Aborted) return fail(DM_ESTATE, "the upstream body this reader followed was aborted");
+        if (s->st == St::Done) {
+            std::shared_ptr<Blob> b = s->blob;
+            g.unlock();
+            if (!b) return fail(DM_ESTATE, "the upstream body this reader followed failed verification");
+            std::lock_guard<std::mutex> g2(e->mu);
+            if (!b->in_hbm) return fail(DM_ENOENT, "blob evicted before the follower switched over");
+            b->readers++;
+            r->blob = b;
+            r->size = b->size;
+            r->follow.reset();
+            return 1;
+        }
+        if (len == 0) return DM_OK;
+        n = (size_t)std::min<uint64_t>(len, s->dma_issued - off);
+        for_segments(e, s->extents, off, n, [&](uint8_t *dev, uint64_t l) { segs.emplace_back(dev, l); });
+    }
+    // the bytes may still be in flight on the body's copy stream: order the read-back after them
+    cudaSetDevice(e->device);
+    Bounce *bn = bounce_get(e);
+    cudaEvent_t ev;
+    cudaError_t err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventRecord(ev, e->copy_stream[s->id % kCopyStreams]);
+    if (err == cudaSuccess) err = cudaStreamWaitEvent(bn->stream, ev, 0);
+    uint8_t *out = static_cast<uint8_t *>(buf);
+    size_t done = 0;
+    for (auto &sg : segs) {
+        uint64_t left = sg.second;
+        uint8_t *dev = sg.first;
+        while (left && err == cudaSuccess) {
+            const size_t m = (size_t)std::min<uint64_t>(left, kBounceBytes);
+            err = cudaMemcpyAsync(bn->host, dev, m, cudaMemcpyDeviceToHost, bn->stream);
+            if (err == cudaSuccess) err = cudaStreamSynchronize(bn->stream);
+            if (err == cudaSuccess) memcpy(out + done, bn->host, m);
+            done += m; dev += m; left -= m;
+        }
+    }
+    if (ev) cudaEventDestroy(ev);
+    bounce_put(e, bn);
+    if (err != cudaSuccess) return fail_cuda(err, "follow_read D2H");
+    e->st_d2h += done; e->st_served += done;
+    if (nread) *nread = done;
+    return DM_OK;
+}
+
 // Start the D2H of [start, start + <=4 MiB) of the blob into a read-ahead window.
 static cudaError_t window_fill(dm_engine *e, Reader *r, Window &w, uint64_t start)
 {
@@ -1724,6 +1800,10 @@ int dm_cache_read(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t
     std::shared_ptr<Reader> r = find_reader(e, reader);
     if (!r) return fail(DM_EINVAL, "unknown reader id");
     if (nread) *nread = 0;
+    if (r->follow) {
+        int rc = follow_read(e, r.get(), off, buf, len, nread);
+        if (rc != 1) return rc;                 // 1: the body completed and was published: fall through to the blob
+    }
     if (off > r->size) return fail(DM_ERANGE, "offset beyond blob end");
     len = (size_t)std::min<uint64_t>(len, r->size - off);
     if (len == 0) return DM_OK;
@@ -1851,6 +1931,31 @@ int dm_cache_close(dm_engine *e, uint64_t reader)
         r->blob->readers--;
     }
     if (r->fd >= 0) close(r->fd);
+    return DM_OK;
+}
+
+int dm_cache_follow(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size_hint)
+{
+    if (!e || !digest || !reader) return fail(DM_EINVAL, "null argument");
+    Digest d;
+    memcpy(d.b, digest, 32);
+    auto r = std::make_shared<Reader>();
+    uint64_t id;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        auto it = e->inflight.find(d);
+        if (it == e->inflight.end()) return DM_ENOENT;
+        r->follow = it->second.lock();
+        if (!r->follow) { e->inflight.erase(it); return DM_ENOENT; }
+        id = e->next_id++;
+    }
+    r->size = r->follow->size_hint;
+    {
+        std::lock_guard<std::mutex> g(e->reader_mu[id % kStripes]);
+        e->readers[id % kStripes][id] = r;
+    }
+    *reader = id;
+    if (size_hint) *size_hint = r->size;
     return DM_OK;
 }
 

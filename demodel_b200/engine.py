@@ -167,6 +167,15 @@ class Engine:
         check(rc, "dm_cache_open")
         return rid.value, size.value
 
+    def cache_follow(self, digest: bytes) -> Optional[tuple[int, int]]:
+        """Attach to a body that is still being ingested (request coalescing): (reader, size_hint) or None."""
+        rid, size = C.c_uint64(), C.c_uint64()
+        rc = self._lib.dm_cache_follow(self._h, _digest_arg(digest), C.byref(rid), C.byref(size))
+        if rc == DM_ENOENT:
+            return None
+        check(rc, "dm_cache_follow")
+        return rid.value, size.value
+
     def cache_read(self, rid: int, off: int, n: int) -> bytes:
         out = np.empty(n, dtype=np.uint8)
         got = C.c_size_t()

@@ -370,3 +370,14 @@ func (r *HitReader) Meta() (string, error) {
 	}
 	return string(buf[:int(n)]), nil
 }
+
+// Follow attaches to a body another connection is ingesting right now
+// (request coalescing); nil if nothing is in flight for this digest.
+func (p *Pool) Follow(digest *[32]byte) *HitReader {
+	e := p.engineFor(digest)
+	var id, size C.uint64_t
+	if C.dm_cache_follow(e, (*C.uint8_t)(unsafe.Pointer(&digest[0])), &id, &size) != C.DM_OK {
+		return nil
+	}
+	return &HitReader{e: e, id: id, Size: int64(size)} // Size 0 = unknown: send chunked
+}

@@ -168,6 +168,14 @@ int dm_cache_read(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t
 int dm_cache_meta(dm_engine *e, uint64_t reader, char *buf, size_t cap, size_t *len);
 int dm_cache_close(dm_engine *e, uint64_t reader);
 int dm_cache_evict(dm_engine *e, const uint8_t digest[32]);   /* HBM tier only; disk copy stays */
+/* Request coalescing: the blob is not cached yet but another connection is
+ * ingesting it right now (a stream opened with this expected digest).  The
+ * reader follows that body out of HBM: dm_cache_read blocks until bytes past
+ * `off` have arrived, and once the body completes and verifies the reader
+ * becomes an ordinary cache reader.  If the body is aborted or fails
+ * verification, reads fail with DM_ESTATE.  DM_ENOENT: nothing in flight.
+ * *size_hint = the Content-Length the ingesting stream was opened with (0 = unknown). */
+int dm_cache_follow(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size_hint);
 
 /* ---- device-resident ingest -------------------------------------------- */
 /* Hash-and-cache n blobs whose bytes are ALREADY in this GPU's HBM (landed
