@@ -81,3 +81,32 @@ def test_product_generator_matches_oracle_generator(oracle):
     seed = 0xDE40DE1
     for blob, off, n in [(0, 0, 4096), (3, 5, 1000), (9, 8, 64), (2, 1 << 33, 777), (1, 123457, 33)]:
         assert np.array_equal(demodel_b200.synth_fill_host(seed, blob, off, n), oracle.blob(seed, blob, off, n))
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary must be bindable from cgo: the header has to compile as C99, not only as C++."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "demodel_b200.h"\n'
+                   'int main(void) { dm_config c; dm_stats s; dm_checkpoint k; dm_layer l;\n'
+                   '  (void)c; (void)s; (void)k; (void)l; return (int)sizeof(dm_config) == 48 ? 0 : 1; }\n')
+    exe = tmp_path / "use_header"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-o", str(exe), str(src)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_reference_arm_runs_without_a_gpu():
+    """bench.py --impl reference is the CPU arm: it must run (and print the contract's keys) on a box
+    with no GPU at all."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().split("\n")[-1])
+    assert line["impl"] == "reference" and line["unit"] == "GB/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["higher_is_better"] is True and line["config"]["workload"] == "tiny"
