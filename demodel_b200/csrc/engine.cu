@@ -269,6 +269,10 @@ struct dm_engine {
     std::vector<Bounce *> bounce_free;
     std::vector<Bounce> bounce_store;
 
+    std::mutex ckpt_mu;              // checkpoint state transfers: pinned staging + own stream, fully synchronous
+    uint32_t *ckpt_pinned = nullptr;
+    cudaStream_t ckpt_stream{};
+
     std::mutex ingest_mu;            // dm_ingest_device scratch
     uint32_t *ing_states = nullptr;
     uint32_t *ing_digests = nullptr;       // device
@@ -1185,6 +1189,8 @@ void dm_engine_destroy(dm_engine *e)
     for (Bounce &b : e->bounce_store) { if (b.host) cudaFreeHost(b.host); if (b.stream) cudaStreamDestroy(b.stream); }
     if (e->ing_states) { cudaFree(e->ing_states); cudaFree(e->ing_digests); cudaFree(e->ing_jobs_d);
                          cudaFreeHost(e->ing_jobs_h); cudaFreeHost(e->ing_digests_h); }
+    if (e->ckpt_stream) cudaStreamDestroy(e->ckpt_stream);
+    if (e->ckpt_pinned) cudaFreeHost(e->ckpt_pinned);
     if (e->ing_ev0) cudaEventDestroy(e->ing_ev0);
     if (e->ing_ev1) cudaEventDestroy(e->ing_ev1);
     if (e->d_states) cudaFree(e->d_states);
@@ -1247,6 +1253,8 @@ int dm_engine_create(const dm_config *cfg, dm_engine **out)
     for (int i = 0; i < kCopyStreams; ++i) CU_INIT(cudaStreamCreateWithFlags(&e->copy_stream[i], cudaStreamNonBlocking));
     CU_INIT(cudaStreamCreateWithFlags(&e->ingest_stream, cudaStreamNonBlocking));
     CU_INIT(cudaStreamCreateWithFlags(&e->util_stream, cudaStreamNonBlocking));
+    CU_INIT(cudaStreamCreateWithFlags(&e->ckpt_stream, cudaStreamNonBlocking));
+    CU_INIT(cudaHostAlloc(&e->ckpt_pinned, 64, cudaHostAllocDefault));
     CU_INIT(cudaEventCreate(&e->ing_ev0));
     CU_INIT(cudaEventCreate(&e->ing_ev1));
 
@@ -1489,7 +1497,10 @@ int dm_stream_checkpoint(dm_engine *e, uint64_t id, dm_checkpoint *out)
         return DM_OK;
     }
     cudaSetDevice(e->device);
-    CU_TRY(cudaMemcpy(out->h, e->d_states + 8ull * s->slot, 32, cudaMemcpyDeviceToHost));
+    std::lock_guard<std::mutex> gc(e->ckpt_mu);
+    CU_TRY(cudaMemcpyAsync(e->ckpt_pinned, e->d_states + 8ull * s->slot, 32, cudaMemcpyDeviceToHost, e->ckpt_stream));
+    CU_TRY(cudaStreamSynchronize(e->ckpt_stream));
+    memcpy(out->h, e->ckpt_pinned, 32);
     return DM_OK;
 }
 
@@ -1503,10 +1514,22 @@ int dm_stream_resume(dm_engine *e, const dm_checkpoint *ck, const uint8_t expect
     Stream *s = sp.get();
     std::lock_guard<std::mutex> g(s->mu);
     s->resume_base = s->dma_issued = s->hash_issued = ck->bytes;
+    if (ck->bytes && s->has_expect) {
+        // not followable: the prefix may never be re-supplied, so there is nothing to serve from offset 0
+        std::lock_guard<std::mutex> g2(e->mu);
+        auto it = e->inflight.find(s->expect);
+        if (it != e->inflight.end() && it->second.lock() == sp) e->inflight.erase(it);
+    }
     if (ck->bytes) {
+        // The state must be IN device memory before this returns: the stream's first job may launch at
+        // once on another CUDA stream.  (A plain cudaMemcpy from pageable memory returns when the bytes
+        // are staged, not when they have landed — found by tools/soak.py.)
         cudaSetDevice(e->device);
-        cudaError_t err = cudaMemcpy(e->d_states + 8ull * s->slot, ck->h, 32, cudaMemcpyHostToDevice);
-        if (err != cudaSuccess) { s->st = St::Aborted; return fail_cuda(err, "cudaMemcpy(checkpoint state)"); }
+        std::lock_guard<std::mutex> gc(e->ckpt_mu);
+        memcpy(e->ckpt_pinned, ck->h, 32);
+        cudaError_t err = cudaMemcpyAsync(e->d_states + 8ull * s->slot, e->ckpt_pinned, 32, cudaMemcpyHostToDevice, e->ckpt_stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(e->ckpt_stream);
+        if (err != cudaSuccess) { s->st = St::Aborted; return fail_cuda(err, "cudaMemcpyAsync(checkpoint state)"); }
     }
     return DM_OK;
 }
