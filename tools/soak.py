@@ -183,7 +183,12 @@ def worker(eng, tid, deadline):
 
 
 def main():
-    eng = demodel_b200.Engine(device=0, hbm_cas_bytes=96 << 20, ring_bytes=24 << 20, slab_bytes=1 << 20, max_streams=4096)
+    cas_dir = os.environ.get("CAS_DIR")                # e.g. /dev/shm/dm_soak: adds spill threads, disk-tier hits
+    if cas_dir:
+        import shutil
+        shutil.rmtree(cas_dir, ignore_errors=True)
+    eng = demodel_b200.Engine(device=0, hbm_cas_bytes=96 << 20, ring_bytes=24 << 20, slab_bytes=1 << 20, max_streams=4096,
+                              cas_dir=cas_dir)
     deadline = time.time() + SECONDS
     ths = [threading.Thread(target=worker, args=(eng, t, deadline)) for t in range(THREADS)]
     for t in ths:
@@ -207,6 +212,17 @@ def main():
         print(e_)
     if alive:
         print(f"{len(alive)} worker(s) hung")
+    if cas_dir and ok:                                  # every file of the disk tier must hash to its own name
+        bad = n_files = 0
+        for root, _, files in os.walk(os.path.join(cas_dir, "blobs", "sha256")):
+            for f in files:
+                if f.endswith(".meta") or f.endswith(".part"):
+                    continue
+                n_files += 1
+                if hashlib.sha256(open(os.path.join(root, f), "rb").read()).hexdigest() != f:
+                    bad += 1
+        print(f"disk tier: {n_files} files, {bad} with a wrong digest")
+        ok = ok and bad == 0 and n_files > 0
     print("SOAK", "OK" if ok else "FAILED")
     if not alive:
         eng.close()
