@@ -1,25 +1,36 @@
 // Multi-buffer SHA-256 for sm_100a: the hot path of the blob hash-and-cache
 // engine.  Pure 32-bit integer work (SHF / LOP3 / IADD3 / IMAD) — no tensor
-// cores, no floating point.  Two kernels share the round function:
+// cores, no floating point.  Three kernel shapes share the round function;
+// the engine picks one per launch from the number of co-resident streams
+// (streams_per_warp_for, crossovers measured on B200):
 //
-//   sha256_wide_kernel  one 32-bit lane per live stream (the multi-buffer
-//                       form north_star describes): W[16] and the eight
-//                       state words live in registers, round constants are
-//                       instruction immediates, each lane pulls one whole
-//                       128-byte line (two blocks) per iteration.  Throughput
-//                       bound by the ALU/FMA issue rate; needs >~10^4 streams
-//                       to fill the chip.
-//   sha256_deep_kernel  one warp per stream, for few live streams.  SHA-256's
-//                       serial chain is only the 64 rounds; the message
-//                       schedule is state-independent.  The 32 lanes expand
-//                       the schedules of 32 consecutive blocks in parallel
-//                       (coalesced 2 KiB load) and stage W[t]+K[t] in shared
-//                       memory; then the warp runs the 32x64 dependent rounds
-//                       reading one broadcast LDS.128 per 4 rounds.  ~1.5x the
-//                       per-stream rate of the lane-per-stream form.
+//   sha256_wide_kernel   one 32-bit lane per live stream (the multi-buffer
+//                        form north_star describes): W[16] and the eight
+//                        state words live in registers, each lane pulls one
+//                        whole 128-byte line (two blocks) per iteration.  The
+//                        shipped variant rolls the rounds 16 at a time (round
+//                        constants from the constant bank; the fully unrolled
+//                        form stalled on the instruction cache) and issues the
+//                        additions on the FMA pipe.  Bound by the ALU pipe
+//                        (one warp-instruction per 2 cycles per sub-partition):
+//                        <= 1.15 TB/s per B200, 0.95 measured; needs > ~10^4
+//                        streams to fill the chip.
+//   sha256_deep_kernel   one warp per stream, for few live streams.  SHA-256's
+//                        serial chain is only the 64 rounds; the message
+//                        schedule is state-independent.  The 32 lanes expand
+//                        the schedules of 32 consecutive blocks in parallel
+//                        (coalesced 2 KiB load) and stage W[t]+K[t] in shared
+//                        memory; then the warp runs the 32x64 dependent rounds
+//                        reading one broadcast LDS.128 per 4 rounds.  ~1.6x the
+//                        per-stream rate of the lane-per-stream form (63 MB/s).
+//   sha256_group_kernel  S = 2/4/8/16 streams per warp: the deep kernel's two
+//                        phases with lane = block_slot * S + stream, so S round
+//                        chains advance per instruction.  Wins between ~640 and
+//                        ~12 000 streams.
 //
-// Both optionally write every byte they read to `dst` (the blob's CAS
-// extent), so hash-and-cache moves 1 B read + 1 B written per blob byte.
+// All optionally write every byte they read to `dst` (the blob's CAS
+// extent), so hash-and-cache moves 1 B read + 1 B written per blob byte;
+// all pad the final block on the device (FIPS 180-4 §5.1.1).
 //
 // The digest definition is FIPS 180-4 (what Go crypto/sha256 implements —
 // the reference names it in BASELINE.json north_star but holds no call site:
