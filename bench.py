@@ -478,6 +478,13 @@ def main():
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_blob_byte": bytes_per_blob_byte, "kernel_ms_per_step": kernel_ms_max / args.steps},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "probes": probes,
+            "notes": {
+                "workload_choice": "BASELINE configs[2] (256 x 64 MiB, 17.18 GB) is the largest single-GPU configuration; "
+                                   "configs[1] (4 Llama-3-8B shards, 16.06 GB) is selectable with --workload llama3_8b_shards",
+                "configs1_expectation": "SHA-256 chains block to block, so 4 blobs are 4 serial chains: measured 0.254 GB/s on "
+                                        "4 x 1 GiB (63.5 MB/s per stream), i.e. ~79 s per pass over the real shard set",
+                "binding_bound": "integer ALU issue (~1.15 TB/s per B200 for SHA-256), not HBM; see DESIGN.md section 5",
+            },
             "host": {"cpus": os.cpu_count(), "cpu_quota": _cpu_quota(), "kernel_variant": os.environ.get("DM_KERNEL_VARIANT")},
         }
         print(json.dumps(line), flush=True)
