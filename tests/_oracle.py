@@ -38,6 +38,9 @@ class Oracle:
         self.base.dmb_hash_and_cache.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t,
                                                  C.c_int, C.c_void_p]
         self.base.dmb_hash_and_cache.restype = C.c_double
+        self.base.dmb_hash_and_cache_files.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint32, C.c_size_t,
+                                                       C.c_int, C.c_void_p]
+        self.base.dmb_hash_and_cache_files.restype = C.c_double
 
     @staticmethod
     def _arr(data) -> np.ndarray:
@@ -96,6 +99,17 @@ class Oracle:
         out = np.zeros(32 * max(n, 1), dtype=np.uint8)
         cptr = cache.ctypes.data if cache is not None else None
         secs = self.base.dmb_hash_and_cache(src.ctypes.data, cptr, off.ctypes.data, n, chunk, threads, out.ctypes.data)
+        return secs, [out[32 * i:32 * i + 32].tobytes() for i in range(n)]
+
+
+    def hash_and_cache_files(self, src: np.ndarray, offsets, directory: str, chunk: int = 32768, threads: int = 1):
+        """The CPU arm with the cache on a filesystem (tmpfs): returns (seconds, digests)."""
+        off = np.ascontiguousarray(np.asarray(offsets, dtype=np.uint64))
+        n = len(off) - 1
+        out = np.zeros(32 * max(n, 1), dtype=np.uint8)
+        os.makedirs(directory, exist_ok=True)
+        secs = self.base.dmb_hash_and_cache_files(src.ctypes.data, directory.encode(), off.ctypes.data, n, chunk, threads,
+                                                  out.ctypes.data)
         return secs, [out[32 * i:32 * i + 32].tobytes() for i in range(n)]
 
 

@@ -111,3 +111,15 @@ def test_blob_generator_is_deterministic_and_offset_consistent(oracle):
     big = oracle.blob(seed, 1, 0, 1 << 16)
     counts = np.bincount(big, minlength=256)
     assert counts.min() > 150 and counts.max() < 370
+
+
+def test_cpu_baseline_file_variant(oracle, tmp_path):
+    # BASELINE.md's form of the CPU arm: cache = content-addressed files
+    rng = np.random.default_rng(6)
+    sizes = [70000, 0, 32768, 5]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    src = rng.integers(0, 256, size=int(off[-1]), dtype=np.uint8)
+    secs, digs = oracle.hash_and_cache_files(src, off, str(tmp_path), threads=2)
+    assert secs >= 0 and digs == oracle.sha256_many(src, off)
+    for i, d in enumerate(digs):
+        assert (tmp_path / d.hex()).read_bytes() == src[int(off[i]):int(off[i + 1])].tobytes()
