@@ -1,3 +1,4 @@
+# NOTE: written when DM_KERNEL_VARIANT took a single fma digit (0 = ptxas choice, 1 = adds on the FMA pipe); still valid: 0 and 1 are style-0 variants.
 mkdir -p gpurun_out
 # launch list (cold-cache, serialised) of the default bench command, short
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_default.csv python bench.py --blobs 256 --blob-bytes 4194304 --steps 2 --warmup 3 --no-cpu > gpurun_out/launches_default.log 2>&1
