@@ -83,6 +83,7 @@ SIGNATURES = {
     "dm_strerror": (C.c_char_p, [C.c_int]),
     "dm_last_error": (C.c_char_p, []),
     "dm_shard_of": (C.c_uint32, [_P, C.c_uint32]),
+    "dm_streams_per_warp": (C.c_uint32, [C.c_uint32]),
     "dm_stream_open": (C.c_int, [_P, _P, C.c_uint64, _U64P]),
     "dm_stream_write": (C.c_int, [_P, C.c_uint64, _P, C.c_size_t]),
     "dm_stream_write_at": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, C.c_size_t]),

@@ -1151,6 +1151,8 @@ int dm_device_count(void)
     return n;
 }
 
+uint32_t dm_streams_per_warp(uint32_t n_resident) { return (uint32_t)dm::streams_per_warp_for(n_resident); }
+
 uint32_t dm_shard_of(const uint8_t digest[32], uint32_t n_shards)
 {
     if (!digest || n_shards <= 1) return 0;

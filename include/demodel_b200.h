@@ -103,6 +103,10 @@ int         dm_engine_stats(dm_engine *e, dm_stats *out);
 const char *dm_strerror(int err);
 const char *dm_last_error(void);                         /* thread-local detail text */
 
+/* Kernel shape the engine picks for `n_resident` co-resident streams: streams per
+ * warp, 1 = warp-per-stream (deep), 2..16 = group, 32 = lane-per-stream (wide).  Pure function. */
+uint32_t    dm_streams_per_warp(uint32_t n_resident);
+
 /* Digest-prefix sharding: which of n_shards engines owns a
  * blob.  Uses the leading 16 bits so any n_shards (not only powers of two)
  * splits the digest space evenly; for n = 2,4,8 it equals digest[0] >> (8-log2 n). */

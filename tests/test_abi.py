@@ -110,3 +110,43 @@ def test_reference_arm_runs_without_a_gpu():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["higher_is_better"] is True and line["config"]["workload"] == "tiny"
+
+
+def test_kernel_selection_rule_and_bench_mirror():
+    """streams_per_warp_for(): monotone, powers of two, deep for the BASELINE 256-stream config, wide for
+    >= 12 289 streams; bench.py's report label mirrors it."""
+    import importlib.util
+    lib = demodel_b200.load()
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    prev = 0
+    for n in list(range(1, 20000, 37)) + [256, 640, 641, 3072, 3073, 6144, 6145, 12288, 12289, 151552, 1 << 31]:
+        spw = lib.dm_streams_per_warp(n)
+        assert spw in (1, 4, 8, 16, 32)
+        label = bench._kernel_for(n)
+        assert (f"{spw} stream" in label)
+    for n in sorted(list(range(1, 20000, 37)) + [640, 641, 3072, 3073, 6144, 6145, 12288, 12289]):
+        spw = lib.dm_streams_per_warp(n)
+        assert spw >= prev
+        prev = spw
+    assert lib.dm_streams_per_warp(256) == 1 and lib.dm_streams_per_warp(12289) == 32 and lib.dm_streams_per_warp(4096) == 8
+
+
+def test_bench_rank_partition_is_disjoint_and_complete():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for world in (2, 4, 8):
+        sets = [bench._my_blob_indices(64, r, world) for r in range(world)]
+        assert all(len(s_) == 64 for s_ in sets)                       # weak scaling: same work per rank
+        flat = [i for s_ in sets for i in s_]
+        assert len(set(flat)) == len(flat)                             # no blob is hashed by two ranks
+        top = max(flat)
+        owners = {i: r for r, s_ in enumerate(sets) for i in s_}
+        from demodel_b200.shard import owner_of_url
+        assert all(owner_of_url(f"synthetic://blob/{i}", world) == r for i, r in owners.items())
+        assert top < 64 * world * 3
+    assert bench._my_blob_indices(5, 0, 1) == [0, 1, 2, 3, 4]
+    assert bench._layout([1, 256, 257])[0] == [0, 256, 512] and bench._layout([1, 256, 257])[1] == 1024
