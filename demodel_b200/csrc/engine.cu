@@ -1,20 +1,27 @@
 // The blob hash-and-cache engine behind include/demodel_b200.h.
 //
-// Data path (DESIGN.md §3):
+// Data path (DESIGN.md §4):
 //
 //   dm_stream_write ──memcpy──▶ pinned ring slab ──one H2D DMA per slab──▶ the blob's
 //   (many threads)              (per stream)        (copy streams)         CAS extent in HBM
 //                                                                               │
-//   pump thread: every cycle gathers all streams with unhashed bytes into one   ▼
-//   job table and launches ONE multi-buffer SHA-256 kernel over them      sha256_{wide,deep}
-//   (hash stream, ordered after the DMAs by an event); finished streams   (reads each byte once)
-//   get their digest through mapped pinned memory, are compared with the
-//   expected oid and published in the CAS index; the spill thread writes
-//   published blobs to the on-disk tier with D2H copies on a side stream.
+//   pump thread: gathers the streams with unhashed bytes into a job table       ▼
+//   (one slab-sized job per stream, at most one in flight per stream) and  sha256_{deep,group,wide}
+//   launches ONE multi-buffer SHA-256 kernel over them; up to 8 launches   (reads each byte once)
+//   overlap on separate CUDA streams, each ordered after the DMAs by an
+//   event.  Finished streams get their digest through mapped pinned memory,
+//   are compared with the expected oid and published in the CAS index; spill
+//   threads write published blobs to the disk tier with D2H copies on side
+//   streams; readers (hits, followers of in-flight bodies) copy out through
+//   pinned read-ahead windows.
 //
 // The bytes land at their final CAS address straight from the DMA, so the
 // ring path costs HBM one write (DMA) + one read (hash) per blob byte.  The
 // device-resident path (dm_ingest_device) fuses the copy into the hash kernel.
+//
+// Lock order (outer → inner): reader.mu → stream.mu → {arena_mu, e->mu, work_mu};
+// slab_mu → work_mu; stripe / reader-stripe mutexes are leaves taken alone.
+// The pump never holds work_mu while taking a stream mutex.
 //
 // Reference hooks served: cmd/demodel/start.go:201-204 (ingest) and
 // start.go:197-200 (hit serving); see include/demodel_b200.h.
