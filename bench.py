@@ -78,6 +78,32 @@ def _kernel_for(n):
     return "wide (32 streams/warp)"
 
 
+def _numa_bind(local_rank):
+    """Opt-in (--numa-bind): pin this process (and every thread it creates later: pump, spill, connection
+    workers) to the CPUs of the NUMA node its GPU hangs off, so the pinned ring and the host buffers are
+    first-touched there.  Returns a description or None if the topology is not visible."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=20).stdout.strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"gpu_bus": bus, "numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def _layout(sizes):
     offs, pos = [], 0
     for s in sizes:
@@ -225,6 +251,7 @@ def main():
     ap.add_argument("--slab-kib", type=int, default=1024)
     ap.add_argument("--e2e-concurrency", type=int, default=256)
     ap.add_argument("--e2e-threads", type=int, default=0)
+    ap.add_argument("--numa-bind", action="store_true", help="pin the process to the GPU's NUMA node (experiment)")
     ap.add_argument("--blobs", type=int, default=0, help="override: number of blobs (with --blob-bytes)")
     ap.add_argument("--blob-bytes", type=int, default=0)
     args = ap.parse_args()
@@ -241,6 +268,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    numa = _numa_bind(local) if args.numa_bind else None
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -498,7 +526,8 @@ def main():
                                         "4 x 1 GiB (63.5 MB/s per stream), i.e. ~79 s per pass over the real shard set",
                 "binding_bound": "integer ALU issue (~1.15 TB/s per B200 for SHA-256), not HBM; see DESIGN.md section 5",
             },
-            "host": {"cpus": os.cpu_count(), "cpu_quota": _cpu_quota(), "kernel_variant": os.environ.get("DM_KERNEL_VARIANT")},
+            "host": {"cpus": os.cpu_count(), "cpu_quota": _cpu_quota(), "kernel_variant": os.environ.get("DM_KERNEL_VARIANT"),
+                     "numa_bind": numa},
         }
         print(json.dumps(line), flush=True)
     eng.close()
