@@ -127,7 +127,7 @@ struct Walker {
                 auto hx = [](char c) { return c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10
                                               : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1; };
                 const int hi = hx(digest[7 + 2 * i]), lo = hx(digest[8 + 2 * i]);
-                if (hi < 0 || lo < 0) is_desc = false;
+                if (hi < 0 || lo < 0) { is_desc = false; break; }
                 L.digest[i] = (uint8_t)((hi << 4) | lo);
             }
             L.size = size;

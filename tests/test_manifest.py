@@ -113,3 +113,44 @@ def test_ollama_pull_at_the_fixture_sizes(oracle, golden_dir):
     finally:
         for e in engines:
             e.close()
+
+
+def test_parser_survives_mutated_and_random_input(golden_dir):
+    """dm_manifest_parse eats bytes from the network: whatever it is fed it must return DM_OK or
+    DM_EINVAL — never crash, hang or read out of bounds."""
+    import ctypes as C
+    import random
+    from demodel_b200._lib import DM_EINVAL, DM_OK, DmLayer
+    lib = demodel_b200.load()
+    fx = json.load(open(os.path.join(golden_dir, "reference_fixture.json")))
+    good = gzip.decompress(bytes.fromhex(fx["gzip_body_hex"]))
+    rnd = random.Random(7)
+    arr = (DmLayer * 8)()
+    n = C.c_uint32()
+    seen_ok = seen_bad = 0
+    for it in range(4000):
+        kind = it % 4
+        if kind == 0:                                   # random bytes
+            blob = bytes(rnd.getrandbits(8) for _ in range(rnd.randrange(0, 200)))
+        elif kind == 1:                                 # truncation
+            blob = good[:rnd.randrange(0, len(good))]
+        elif kind == 2:                                 # byte flips
+            b = bytearray(good)
+            for _ in range(rnd.randrange(1, 6)):
+                b[rnd.randrange(len(b))] = rnd.getrandbits(8)
+            blob = bytes(b)
+        else:                                           # structural noise: deep nesting, huge numbers, odd escapes
+            blob = (b"[" * rnd.randrange(0, 200) + rnd.choice([b'{"size":1e999,"digest":"sha256:zz"}', b'"\\u12', b"-",
+                    b'{"a":{"digest":"sha256:' + b"ab" * 32 + b'","size":18446744073709551616}}', good]) +
+                    b"]" * rnd.randrange(0, 200))
+        rc = lib.dm_manifest_parse(blob, len(blob), arr, 8, C.byref(n))
+        assert rc in (DM_OK, DM_EINVAL), (rc, blob[:60])
+        if rc == DM_OK:
+            seen_ok += 1
+            assert n.value <= 1000
+        else:
+            seen_bad += 1
+    assert seen_ok > 50 and seen_bad > 500
+    # max_layers smaller than what is found: count is reported, nothing is written past the array
+    rc = lib.dm_manifest_parse(good, len(good), arr, 2, C.byref(n))
+    assert rc == DM_OK and n.value == 4
