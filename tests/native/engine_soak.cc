@@ -1,0 +1,254 @@
+// TEST INFRASTRUCTURE ONLY — multi-threaded soak of the engine's host logic through the C-ABI, linked
+// against the fake synchronous CUDA runtime (fake_cuda.cc) so it runs on a CPU-only box under
+// ThreadSanitizer / AddressSanitizer.  What it checks: routing of bytes (sequential, ranges, zero-copy,
+// unknown size), padding contract, verdicts, cache reads, followers, eviction under a tiny arena, ring
+// back-pressure with a tiny ring, checkpoint/resume, verify-only streams, the disk tier, leak
+// accounting — with real threads, so the sanitizers see the engine's locking as it really runs.
+// Digest arithmetic itself is NOT what this rig proves (the fake kernels use the oracle); the GPU
+// parity tests do that.
+#include "../../include/demodel_b200.h"
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <thread>
+#include <vector>
+
+extern "C" void dmo_sha256(const void *data, size_t len, uint8_t out[32]);
+
+#define CHECK(c) do { if (!(c)) { fprintf(stderr, "FAILED %s:%d: %s (last error: %s)\n", __FILE__, __LINE__, #c, dm_last_error()); \
+                                   failures.fetch_add(1); return; } } while (0)
+
+static std::atomic<int> failures{0};
+static std::atomic<long> ops{0}, enomem{0}, followed{0};
+
+struct Body { std::vector<uint8_t> bytes; uint8_t digest[32]; };
+static std::vector<Body> bodies;
+
+static void make_bodies()
+{
+    const size_t sizes[] = {0, 1, 63, 64, 65, 4096, 65536, 65537, 200000, 300001, 700000, 1500000};
+    for (int rep = 0; rep < 2; ++rep)
+        for (size_t s : sizes) {
+            Body b;
+            b.bytes.resize(s);
+            dm_synth_fill_host(0xDE40DE1, 500 + bodies.size(), 0, b.bytes.data(), s);
+            dmo_sha256(b.bytes.data(), s, b.digest);
+            bodies.push_back(std::move(b));
+        }
+}
+
+static bool tolerate(int rc) { if (rc == DM_ENOMEM) { enomem++; return true; } return false; }
+
+// finish (optionally flushing first); a full arena at the last slab is legal: abort and report "skipped"
+static int finish_or_skip(dm_engine *e, uint64_t id, bool flush_first, uint8_t got[32], int *matched)
+{
+    int rc = flush_first ? dm_stream_flush(e, id) : DM_OK;
+    if (rc == DM_OK) rc = dm_stream_finish(e, id, got, matched);
+    if (rc == DM_ENOMEM) { enomem++; dm_stream_abort(e, id); return 1; }
+    return rc;
+}
+
+static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
+{
+    std::mt19937_64 rng(1000 + tid);
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::duration<double>(seconds);
+    std::vector<uint8_t> scratch(2 << 20);
+    while (std::chrono::steady_clock::now() < deadline && !failures.load()) {
+        const Body &b = bodies[rng() % bodies.size()];
+        const size_t n = b.bytes.size();
+        const uint8_t *p = b.bytes.data();
+        uint8_t got[32];
+        int matched = -1, rc;
+        uint64_t id = 0;
+        const int op = (int)(rng() % 12);
+        ops++;
+        if (op <= 1) {                                               // sequential, random piece size
+            rc = dm_stream_open(e, b.digest, (rng() & 1) ? n : 0, &id);
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
+            size_t pos = 0;
+            bool dead = false;
+            while (pos < n) {
+                const size_t k = std::min<size_t>(n - pos, 1 + rng() % 90000);
+                rc = dm_stream_write(e, id, p + pos, k);
+                if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); dead = true; break; }
+                pos += k;
+            }
+            if (dead) continue;
+            rc = finish_or_skip(e, id, rng() & 1, got, &matched);
+            if (rc == 1) continue;
+            CHECK(rc == DM_OK);
+            CHECK(matched == 1 && memcmp(got, b.digest, 32) == 0);
+        } else if (op == 2 && n > 1000 && !verify_only) {            // three range parts, pieces interleaved
+            rc = dm_stream_open(e, b.digest, n, &id);
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
+            size_t cut1 = 1 + rng() % (n - 2), cut2 = cut1 + rng() % (n - cut1);
+            size_t lo[3] = {0, cut1, cut2}, hi[3] = {cut1, cut2, n};
+            bool dead = false;
+            while (!dead && (lo[0] < hi[0] || lo[1] < hi[1] || lo[2] < hi[2])) {
+                const int k = (int)(rng() % 3);
+                if (lo[k] >= hi[k]) continue;
+                const size_t m = std::min<size_t>(hi[k] - lo[k], 1 + rng() % 70000);
+                rc = dm_stream_write_at(e, id, lo[k], p + lo[k], m);
+                if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); dead = true; }
+                lo[k] += m;
+            }
+            if (dead) continue;
+            rc = finish_or_skip(e, id, false, got, &matched);
+            if (rc == 1) continue;
+            CHECK(rc == DM_OK);
+            CHECK(matched == 1 && memcmp(got, b.digest, 32) == 0);
+        } else if (op == 3) {                                        // zero-copy windows
+            rc = dm_stream_open(e, b.digest, n, &id);
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
+            size_t pos = 0;
+            bool dead = false;
+            while (pos < n) {
+                void *win = nullptr;
+                size_t cap = 0;
+                rc = dm_stream_acquire(e, id, &win, &cap);
+                if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); dead = true; break; }
+                const size_t k = std::min<size_t>(std::min(cap, n - pos), 1 + rng() % 50000);
+                memcpy(win, p + pos, k);
+                rc = dm_stream_commit(e, id, k);
+                if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); dead = true; break; }
+                pos += k;
+            }
+            if (dead) continue;
+            rc = finish_or_skip(e, id, false, got, &matched);
+            if (rc == 1) continue;
+            CHECK(rc == DM_OK);
+            CHECK(matched == 1 && memcmp(got, b.digest, 32) == 0);
+        } else if (op == 4) {                                        // client goes away
+            rc = dm_stream_open(e, b.digest, n, &id);
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
+            rc = dm_stream_write(e, id, p, n / 2);
+            CHECK(rc == DM_OK || tolerate(rc));
+            CHECK(dm_stream_abort(e, id) == DM_OK);
+        } else if (op == 5) {                                        // wrong oid must be caught
+            uint8_t wrong[32];
+            memset(wrong, 0x5a, 32);
+            rc = dm_stream_open(e, wrong, n, &id);
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
+            rc = dm_stream_write(e, id, p, n);
+            if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); continue; }
+            rc = finish_or_skip(e, id, false, got, &matched);
+            if (rc == 1) continue;
+            CHECK(rc == DM_OK);
+            CHECK(matched == 0 && memcmp(got, b.digest, 32) == 0);
+        } else if (op == 6 || op == 7) {                             // hit serving, io.Copy style + random reads
+            uint64_t rid = 0, size = 0;
+            if (dm_cache_open(e, b.digest, &rid, &size) != DM_OK) continue;
+            CHECK(size == n);
+            size_t off = 0, nread = 0;
+            const size_t piece = (op == 6) ? 32768 : 1 + rng() % 300000;
+            while (off < n) {
+                CHECK(dm_cache_read(e, rid, off, scratch.data(), std::min(piece, scratch.size()), &nread) == DM_OK);
+                CHECK(nread > 0 && memcmp(scratch.data(), p + off, nread) == 0);
+                off += nread;
+                if (op == 7 && n) off = std::min<size_t>(n, off + rng() % 1000);     // skip around a little
+            }
+            char meta[512];
+            size_t mlen = 0;
+            CHECK(dm_cache_meta(e, rid, meta, sizeof meta, &mlen) == DM_OK && mlen > 10);
+            CHECK(dm_cache_close(e, rid) == DM_OK);
+        } else if (op == 8 && !verify_only) {                        // coalesce onto an in-flight body
+            uint64_t rid = 0, hint = 0;
+            if (dm_cache_follow(e, b.digest, &rid, &hint) != DM_OK) continue;
+            size_t off = 0, nread = 0;
+            bool ok = true;
+            for (;;) {
+                rc = dm_cache_read(e, rid, off, scratch.data(), 100000, &nread);
+                if (rc != DM_OK) { CHECK(rc == DM_ESTATE || rc == DM_ENOENT); ok = false; break; }
+                if (nread == 0) break;
+                CHECK(off + nread <= n && memcmp(scratch.data(), p + off, nread) == 0);
+                off += nread;
+            }
+            if (ok) { CHECK(off == n); followed++; }
+            CHECK(dm_cache_close(e, rid) == DM_OK);
+        } else if (op == 9) {
+            rc = dm_cache_evict(e, b.digest);
+            CHECK(rc == DM_OK || rc == DM_ENOENT || rc == DM_ESTATE);
+        } else if (op == 10 && n > 70000) {                          // interrupted download, resumed
+            const size_t cut = 65000 + rng() % (n - 65000);
+            rc = dm_stream_open(e, b.digest, n, &id);
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
+            rc = dm_stream_write(e, id, p, cut);
+            if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); continue; }
+            dm_checkpoint ck;
+            rc = dm_stream_checkpoint(e, id, &ck);
+            if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); continue; }
+            CHECK(ck.bytes <= cut && ck.bytes % 64 == 0 && (verify_only || ck.bytes == cut / 64 * 64));
+            CHECK(dm_stream_abort(e, id) == DM_OK);
+            rc = dm_stream_resume(e, &ck, b.digest, n, &id);
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
+            if ((rng() & 1) && !verify_only && ck.bytes) {
+                rc = dm_stream_write_at(e, id, 0, p, ck.bytes);
+                if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); continue; }
+            }
+            rc = dm_stream_write(e, id, p + ck.bytes, n - ck.bytes);
+            if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); continue; }
+            rc = finish_or_skip(e, id, false, got, &matched);
+            if (rc == 1) continue;
+            CHECK(rc == DM_OK);
+            CHECK(matched == 1 && memcmp(got, b.digest, 32) == 0);
+        } else if (op == 11) {                                       // metadata + stats are always safe to call
+            dm_stats st;
+            CHECK(dm_engine_stats(e, &st) == DM_OK);
+            CHECK(st.ring_slabs_free <= st.ring_slabs_total);
+            uint64_t sz = 0;
+            rc = dm_cache_contains(e, b.digest, &sz);
+            CHECK(rc == DM_ENOENT || (rc == DM_OK && sz == n));
+        }
+    }
+}
+
+int main(int argc, char **argv)
+{
+    const double seconds = argc > 1 ? atof(argv[1]) : 5.0;
+    const int threads = argc > 2 ? atoi(argv[2]) : 6;
+    const char *cas_dir = argc > 3 && argv[3][0] ? argv[3] : nullptr;
+    const bool verify_only = argc > 4 && atoi(argv[4]) != 0;
+    make_bodies();
+    dm_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = sizeof cfg;
+    cfg.device = 0;
+    cfg.hbm_cas_bytes = 6u << 20;              // tiny arena: eviction and ENOMEM are part of the test
+    cfg.ring_bytes = 1u << 20;                 // 16 slabs of 64 KiB for up to `threads` writers: back-pressure
+    cfg.slab_bytes = 64u << 10;
+    cfg.max_streams = 256;
+    cfg.cas_dir = cas_dir;
+    cfg.flags = verify_only ? DM_F_NO_HBM_CAS : 0;
+    dm_engine *e = nullptr;
+    if (dm_engine_create(&cfg, &e) != DM_OK) { fprintf(stderr, "create failed: %s\n", dm_last_error()); return 1; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) th.emplace_back(worker, e, t, seconds, verify_only);
+    for (auto &t : th) t.join();
+    dm_stats st;
+    for (int i = 0; i < 500; ++i) {
+        dm_engine_stats(e, &st);
+        if (st.ring_slabs_free == st.ring_slabs_total && st.free_stream_slots == 256) break;
+        std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
+    const bool clean = st.open_streams == 0 && st.open_readers == 0 && st.ring_slabs_free == st.ring_slabs_total &&
+                       st.free_stream_slots == 256;
+    printf("ops=%ld enomem=%ld followed=%ld launches=%llu committed=%llu mismatched=%llu ring_waits=%llu clean=%d failures=%d\n",
+           ops.load(), enomem.load(), followed.load(), (unsigned long long)st.kernel_launches, (unsigned long long)st.blobs_committed,
+           (unsigned long long)st.blobs_mismatched, (unsigned long long)st.ring_waits, (int)clean, failures.load());
+    dm_engine_destroy(e);
+    if (failures.load() || !clean) { printf("ENGINE SOAK FAILED\n"); return 1; }
+    printf("ENGINE SOAK OK\n");
+    return 0;
+}
