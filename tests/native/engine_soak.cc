@@ -214,6 +214,75 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
     }
 }
 
+// The goroutine-model driver (BodyTee / HitReader over the C-ABI) in all its modes, then the
+// manifest-aware prefetch, on an engine of its own so results are deterministic.
+static void driver_phase(bool verify_only)
+{
+    dm_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = sizeof cfg;
+    cfg.hbm_cas_bytes = 64u << 20;
+    cfg.ring_bytes = 2u << 20;
+    cfg.slab_bytes = 64u << 10;
+    cfg.max_streams = 256;
+    cfg.flags = verify_only ? DM_F_NO_HBM_CAS : 0;
+    dm_engine *e = nullptr;
+    CHECK(dm_engine_create(&cfg, &e) == DM_OK);
+    const uint32_t n = (uint32_t)bodies.size();
+    std::vector<uint64_t> off(n + 1, 0);
+    for (uint32_t i = 0; i < n; ++i) off[i + 1] = off[i] + bodies[i].bytes.size();
+    std::vector<uint8_t> host(off[n] ? off[n] : 1), expect(32ull * n), digs(32ull * n), verdict(n), back(host.size());
+    for (uint32_t i = 0; i < n; ++i) {
+        if (!bodies[i].bytes.empty()) memcpy(host.data() + off[i], bodies[i].bytes.data(), bodies[i].bytes.size());
+        memcpy(expect.data() + 32ull * i, bodies[i].digest, 32);
+    }
+    for (int mode = 0; mode <= 4; ++mode) {
+        double secs = 0;
+        std::fill(verdict.begin(), verdict.end(), 9);
+        const int rc = dm_proxy_drive(e, host.data(), off.data(), n, expect.data(), 4096 + 1000 * mode, 8, mode < 2 ? 3 : 0, mode,
+                                      digs.data(), verdict.data(), &secs);
+        CHECK(rc == DM_OK);
+        for (uint32_t i = 0; i < n; ++i) {
+            if (mode == 4) { CHECK(verdict[i] == 2); continue; }
+            CHECK(verdict[i] == 1 && memcmp(digs.data() + 32ull * i, bodies[i].digest, 32) == 0);
+        }
+        if (mode != 4 && !verify_only) {
+            std::fill(back.begin(), back.end(), 0);
+            CHECK(dm_proxy_serve(e, expect.data(), n, back.data(), off.data(), 10000, 4, &secs) == DM_OK);
+            CHECK(memcmp(back.data(), host.data(), off[n]) == 0);
+        }
+        for (uint32_t i = 0; i < n; ++i) dm_cache_evict(e, bodies[i].digest);
+    }
+    if (!verify_only) {                                     // manifest: parse, prefetch, pull, second prefetch = all hits
+        auto hex = [](const uint8_t *d) { std::string s; char t[3]; for (int i = 0; i < 32; ++i) { snprintf(t, 3, "%02x", d[i]); s += t; } return s; };
+        std::string m = "{\"schemaVersion\":2,\"config\":{\"digest\":\"sha256:" + hex(bodies[5].digest) + "\",\"size\":" +
+                        std::to_string(bodies[5].bytes.size()) + "},\"layers\":[";
+        for (int k = 6; k < 10; ++k)
+            m += std::string(k > 6 ? "," : "") + "{\"mediaType\":\"l\",\"digest\":\"sha256:" + hex(bodies[k].digest) + "\",\"size\":" +
+                 std::to_string(bodies[k].bytes.size()) + "}";
+        m += "]}";
+        dm_layer L[8];
+        uint32_t nl = 0;
+        CHECK(dm_manifest_parse(m.data(), m.size(), L, 8, &nl) == DM_OK && nl == 5);
+        uint64_t ids[8];
+        CHECK(dm_manifest_prefetch(e, L, nl, ids) == DM_OK);
+        for (uint32_t i = 0; i < nl; ++i) {
+            CHECK(ids[i] != 0);
+            const Body &b = bodies[5 + i];
+            CHECK(dm_stream_write(e, ids[i], b.bytes.data(), b.bytes.size()) == DM_OK);
+            uint8_t got[32];
+            int matched = 0;
+            CHECK(dm_stream_finish(e, ids[i], got, &matched) == DM_OK && matched == 1);
+        }
+        CHECK(dm_manifest_prefetch(e, L, nl, ids) == DM_OK);
+        for (uint32_t i = 0; i < nl; ++i) CHECK(ids[i] == 0);
+    }
+    dm_stats st;
+    dm_engine_stats(e, &st);
+    CHECK(st.open_streams == 0 && st.open_readers == 0);
+    dm_engine_destroy(e);
+}
+
 int main(int argc, char **argv)
 {
     const double seconds = argc > 1 ? atof(argv[1]) : 5.0;
@@ -248,6 +317,7 @@ int main(int argc, char **argv)
            ops.load(), enomem.load(), followed.load(), (unsigned long long)st.kernel_launches, (unsigned long long)st.blobs_committed,
            (unsigned long long)st.blobs_mismatched, (unsigned long long)st.ring_waits, (int)clean, failures.load());
     dm_engine_destroy(e);
+    if (!failures.load()) driver_phase(verify_only);
     if (failures.load() || !clean) { printf("ENGINE SOAK FAILED\n"); return 1; }
     printf("ENGINE SOAK OK\n");
     return 0;
