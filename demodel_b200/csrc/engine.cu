@@ -166,6 +166,8 @@ struct Stream {
     std::deque<std::pair<Slab *, uint32_t>> staged;
     std::vector<std::pair<std::string, std::string>> meta;   // dm_stream_set_meta
     uint32_t followers = 0;    // readers attached while the body is still arriving (request coalescing)
+    uint32_t follow_reads = 0; // followers' copy-outs in flight: the extents must not be freed or handed over meanwhile
+    bool completing = false;   // digest known, extents being handed to the index: followers wait for Done
     uint64_t size_hint = 0;
     bool window_out = false;   // acquire() window outstanding
     bool queued = false;       // in the pump's inbox / ready list (guarded by mu)
@@ -706,6 +708,12 @@ void evict_many(dm_engine *e, const uint8_t *digests, uint32_t n)
 
 // ---- pump ----------------------------------------------------------------------
 
+// Before a stream's extents are freed or change owner: let followers' in-flight copy-outs finish.
+void wait_follow_reads(Stream *s, std::unique_lock<std::mutex> &g)
+{
+    s->cv.wait(g, [&] { return s->follow_reads == 0; });
+}
+
 void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint32_t *words)
 {
     Stream *s = sp.get();
@@ -713,6 +721,8 @@ void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint
     if (s->st == St::Aborted) return;
     words_to_digest(words, s->digest.b);
     s->matched = (!s->has_expect || s->digest == s->expect) ? 1 : 0;
+    s->completing = true;                       // no new follower copy-out starts past this point
+    wait_follow_reads(s, g);
     std::vector<Extent> ext;
     ext.swap(s->extents);
     s->capacity = 0;
@@ -760,6 +770,7 @@ void reap_cycle(dm_engine *e, Cycle &c)
         if (free_now) {
             // slabs written after this job was built may still be landing in the extent (see dm_stream_abort)
             cudaStreamSynchronize(e->copy_stream[sp->id % kCopyStreams]);
+            { std::unique_lock<std::mutex> g(sp->mu); wait_follow_reads(sp.get(), g); }
             free_extents(e, sp->extents);
             std::lock_guard<std::mutex> g(e->mu);
             e->free_slots.push_back(sp->slot);
@@ -1670,6 +1681,7 @@ int dm_stream_abort(dm_engine *e, uint64_t id)
         // another blob before it lands (the stale copy would overwrite the new owner's bytes).
         cudaSetDevice(e->device);
         cudaStreamSynchronize(e->copy_stream[s->id % kCopyStreams]);
+        { std::unique_lock<std::mutex> g(s->mu); wait_follow_reads(s, g); }
         free_extents(e, s->extents);
     }
     drop_stream(e, sp, free_now);   // otherwise the pump releases slot + extents at reap (after the kernel,
@@ -1764,7 +1776,9 @@ static int follow_read(dm_engine *e, Reader *r, uint64_t off, void *buf, size_t 
     {
         std::unique_lock<std::mutex> g(s->mu);
         s->followers++;
-        s->cv.wait(g, [&] { return s->st == St::Done || s->st == St::Aborted || off < s->dma_issued || len == 0; });
+        s->cv.wait(g, [&] {
+            return s->st == St::Done || s->st == St::Aborted || (off < s->dma_issued && !s->completing) || len == 0;
+        });
         s->followers--;
         if (s->st == St::Aborted) return fail(DM_ESTATE, "the upstream body this reader followed was aborted");
         if (s->st == St::Done) {
@@ -1782,7 +1796,12 @@ static int follow_read(dm_engine *e, Reader *r, uint64_t off, void *buf, size_t 
         if (len == 0) return DM_OK;
         n = (size_t)std::min<uint64_t>(len, s->dma_issued - off);
         for_segments(e, s->extents, off, n, [&](uint8_t *dev, uint64_t l) { segs.emplace_back(dev, l); });
+        s->follow_reads++;                      // pins the extents until the copy-out below is done
     }
+    struct Unpin {
+        Stream *s;
+        ~Unpin() { { std::lock_guard<std::mutex> g(s->mu); s->follow_reads--; } s->cv.notify_all(); }
+    } unpin{s};
     // the bytes may still be in flight on the body's copy stream: order the read-back after them
     cudaSetDevice(e->device);
     Bounce *bn = bounce_get(e);

@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY — see fake_cuda/cuda_runtime.h.  Synchronous fake runtime + the three
+// TEST INFRASTRUCTURE ONLY — see fake_cuda/cuda_runtime.h.  Asynchronous fake runtime (one worker thread per stream) + the three
 // SHA-256 "kernel" launchers executed on the CPU by the oracle (oracle/sha256_oracle.c), honouring
 // exactly the HashJob contract the real kernels implement (INIT / FINAL flags, state table, fused copy).
 #include "fake_cuda/cuda_runtime.h"
@@ -12,11 +12,85 @@ extern "C" {
 #include "../../oracle/sha256_oracle.c"
 }
 
+// ---- asynchronous streams -----------------------------------------------------------------------
+// Each stream is a worker thread draining a FIFO of closures; copies and "kernels" run there, later
+// than the call that enqueued them, so ThreadSanitizer sees any host-side reuse of a buffer that is not
+// ordered after the event guarding it as a data race — exactly the engine's lifetime rules.
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+struct fakeStream {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    bool stop = false, busy = false;
+    std::thread th;
+    fakeStream() : th([this] { run(); }) {}
+    void run()
+    {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> g(mu);
+                cv.wait(g, [&] { return stop || !q.empty(); });
+                if (q.empty()) return;
+                f = std::move(q.front());
+                q.pop_front();
+                busy = true;
+            }
+            f();
+            {
+                std::lock_guard<std::mutex> g(mu);
+                busy = false;
+            }
+            cv.notify_all();
+        }
+    }
+    void push(std::function<void()> f)
+    {
+        { std::lock_guard<std::mutex> g(mu); q.push_back(std::move(f)); }
+        cv.notify_all();
+    }
+    void drain()
+    {
+        std::unique_lock<std::mutex> g(mu);
+        cv.wait(g, [&] { return q.empty() && !busy; });
+    }
+};
+struct EvState {
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t recorded = 0, done = 0;      // generations: a wait targets the record current at the time of the call
+};
+// The handle may be destroyed while work that refers to the event is still queued (legal in CUDA:
+// resources are released when that work completes), so queued closures share ownership of the state.
+struct fakeEvent { std::shared_ptr<EvState> st = std::make_shared<EvState>(); };
+static std::mutex g_reg_mu;
+static std::vector<fakeStream *> g_streams;
+
+static void on_stream(cudaStream_t s, std::function<void()> f)
+{
+    if (!s) { f(); return; }              // legacy stream: synchronous
+    s->push(std::move(f));
+}
+
 extern "C" {
 cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { memset(p, 0, sizeof *p); p->major = 10; p->multiProcessorCount = 148; return cudaSuccess; }
-cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void)
+{
+    std::vector<fakeStream *> all;
+    { std::lock_guard<std::mutex> g(g_reg_mu); all = g_streams; }
+    for (fakeStream *s : all) s->drain();
+    return cudaSuccess;
+}
 cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = 1ull << 30; return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t) { return "fake cuda error"; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
@@ -26,17 +100,68 @@ cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = calloc(1, n ? n :
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaHostGetDevicePointer(void **dev, void *host, unsigned) { *dev = host; return cudaSuccess; }
 cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
-cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStream_t)malloc(1); return cudaSuccess; }
-cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
-cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (cudaEvent_t)malloc(1); return cudaSuccess; }
-cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = (cudaEvent_t)malloc(1); return cudaSuccess; }
-cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t st)
+{
+    on_stream(st, [d, s, n] { memcpy(d, s, n); });
+    return cudaSuccess;
+}
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned)
+{
+    *s = new fakeStream();
+    std::lock_guard<std::mutex> g(g_reg_mu);
+    g_streams.push_back(*s);
+    return cudaSuccess;
+}
+cudaError_t cudaStreamDestroy(cudaStream_t s)
+{
+    if (!s) return cudaSuccess;
+    s->drain();
+    { std::lock_guard<std::mutex> g(s->mu); s->stop = true; }
+    s->cv.notify_all();
+    s->th.join();
+    { std::lock_guard<std::mutex> g(g_reg_mu); for (auto &x : g_streams) if (x == s) { x = g_streams.back(); g_streams.pop_back(); break; } }
+    delete s;
+    return cudaSuccess;
+}
+cudaError_t cudaStreamSynchronize(cudaStream_t s) { if (s) s->drain(); return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new fakeEvent(); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new fakeEvent(); return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t ev, cudaStream_t s)
+{
+    std::shared_ptr<EvState> e = ev->st;
+    uint64_t gen;
+    { std::lock_guard<std::mutex> g(e->mu); gen = ++e->recorded; }
+    on_stream(s, [e, gen] {
+        { std::lock_guard<std::mutex> g(e->mu); if (e->done < gen) e->done = gen; }
+        e->cv.notify_all();
+    });
+    return cudaSuccess;
+}
+cudaError_t cudaEventQuery(cudaEvent_t ev)
+{
+    std::lock_guard<std::mutex> g(ev->st->mu);
+    return ev->st->done >= ev->st->recorded ? cudaSuccess : cudaErrorNotReady;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t ev)
+{
+    std::shared_ptr<EvState> e = ev->st;
+    std::unique_lock<std::mutex> g(e->mu);
+    const uint64_t gen = e->recorded;
+    e->cv.wait(g, [&] { return e->done >= gen; });
+    return cudaSuccess;
+}
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t ev, unsigned)
+{
+    std::shared_ptr<EvState> e = ev->st;
+    uint64_t gen;
+    { std::lock_guard<std::mutex> g(e->mu); gen = e->recorded; }
+    on_stream(s, [e, gen] {
+        std::unique_lock<std::mutex> g(e->mu);
+        e->cv.wait(g, [&] { return e->done >= gen; });
+    });
+    return cudaSuccess;
+}
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.001f; return cudaSuccess; }
 }
 
@@ -70,24 +195,26 @@ static void run_job(const HashJob &jb, uint32_t *states, uint32_t *digests)
     }
 }
 
-static cudaError_t run_all(const HashJob *jobs, uint32_t n, uint32_t *states, uint32_t *digests)
+// the "kernel" runs later, on the stream's thread, reading the job table that an earlier copy on the
+// same stream delivered
+static cudaError_t run_all(const HashJob *jobs, uint32_t n, uint32_t *states, uint32_t *digests, cudaStream_t st)
 {
-    for (uint32_t i = 0; i < n; ++i) run_job(jobs[i], states, digests);
+    on_stream(st, [jobs, n, states, digests] { for (uint32_t i = 0; i < n; ++i) run_job(jobs[i], states, digests); });
     return cudaSuccess;
 }
-cudaError_t launch_sha256_wide(const HashJob *j, uint32_t n, uint32_t *s, uint32_t *d, cudaStream_t, int) { return run_all(j, n, s, d); }
-cudaError_t launch_sha256_deep(const HashJob *j, uint32_t n, uint32_t *s, uint32_t *d, cudaStream_t, int) { return run_all(j, n, s, d); }
-cudaError_t launch_sha256_group(const HashJob *j, uint32_t n, uint32_t *s, uint32_t *d, cudaStream_t, int) { return run_all(j, n, s, d); }
+cudaError_t launch_sha256_wide(const HashJob *j, uint32_t n, uint32_t *s, uint32_t *d, cudaStream_t st, int) { return run_all(j, n, s, d, st); }
+cudaError_t launch_sha256_deep(const HashJob *j, uint32_t n, uint32_t *s, uint32_t *d, cudaStream_t st, int) { return run_all(j, n, s, d, st); }
+cudaError_t launch_sha256_group(const HashJob *j, uint32_t n, uint32_t *s, uint32_t *d, cudaStream_t st, int) { return run_all(j, n, s, d, st); }
 
-cudaError_t launch_synth_fill(uint64_t seed, uint64_t blob, uint64_t off, void *dst, size_t len, cudaStream_t)
+cudaError_t launch_synth_fill(uint64_t seed, uint64_t blob, uint64_t off, void *dst, size_t len, cudaStream_t st)
 {
-    dmo_blob_fill(seed, blob, off, dst, len);
+    on_stream(st, [=] { dmo_blob_fill(seed, blob, off, dst, len); });
     return cudaSuccess;
 }
 cudaError_t launch_synth_fill_many(uint64_t seed, uint64_t first, void *base, const uint64_t *offs, const uint64_t *lens,
-                                   uint32_t n, uint64_t, uint64_t, cudaStream_t)
+                                   uint32_t n, uint64_t, uint64_t, cudaStream_t st)
 {
-    for (uint32_t i = 0; i < n; ++i) dmo_blob_fill(seed, first + i, 0, static_cast<uint8_t *>(base) + offs[i], lens[i]);
+    on_stream(st, [=] { for (uint32_t i = 0; i < n; ++i) dmo_blob_fill(seed, first + i, 0, static_cast<uint8_t *>(base) + offs[i], lens[i]); });
     return cudaSuccess;
 }
 

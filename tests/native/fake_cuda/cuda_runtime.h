@@ -1,8 +1,9 @@
-// TEST INFRASTRUCTURE ONLY — a fake, fully synchronous "CUDA runtime" so that the engine's host
+// TEST INFRASTRUCTURE ONLY — a fake "CUDA runtime" (asynchronous: one worker thread per stream) so that the engine's host
 // logic (demodel_b200/csrc/engine.cu: ring, pump thread, CAS, ranges, followers, disk tier) can be
 // compiled with plain g++ and soaked under ThreadSanitizer / ASan on a box with no GPU.
-// Device memory is host memory, copies are memcpy, streams run inline, events are always complete,
-// and the SHA-256 "kernels" are executed by the CPU oracle (tests/native/fake_cuda.cc).
+// Device memory is host memory; copies and "kernels" run later on the stream's worker thread in FIFO order;
+// events carry record generations (query / synchronize / stream-wait behave like CUDA's); the SHA-256
+// "kernels" are executed by the CPU oracle (tests/native/fake_cuda.cc).
 // Never linked into libdemodel_b200.so; built only by tests/test_native_host.py into a temp dir.
 #pragma once
 #include <cstddef>
