@@ -865,7 +865,7 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
     cudaEventRecord(c.k_start, c.stream);
     if (spw == 1) { dm::launch_sha256_deep(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_deep); e->st_deep++; }
     else if (spw == 32) { dm::launch_sha256_wide(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_wide); e->st_wide++; }
-    else { dm::launch_sha256_group(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, spw); e->st_group++; }
+    else { dm::launch_sha256_group(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, spw, e->variant_deep); e->st_group++; }
     e->st_launches++;
     cudaEventRecord(c.k_end, c.stream);
     c.busy = true;
@@ -1250,7 +1250,7 @@ int dm_engine_create(const dm_config *cfg, dm_engine **out)
         int w = -1, d = -1;
         if (sscanf(v, "%d,%d", &w, &d) >= 1) {
             if (w >= 0 && w < 20) e->variant_wide = w;
-            if (d >= 0 && d <= 3) e->variant_deep = d;
+            if (d >= 0 && d <= 4) e->variant_deep = d;   // 4 = short-chain round (deep and group kernels)
         }
     }
     if (!e->cfg.slab_bytes) e->cfg.slab_bytes = 1u << 20;
@@ -2116,7 +2116,7 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
     if (err == cudaSuccess)
         err = spw == 1 ? dm::launch_sha256_deep(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, e->variant_deep)
             : spw == 32 ? dm::launch_sha256_wide(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, e->variant_wide)
-                        : dm::launch_sha256_group(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, spw);
+                        : dm::launch_sha256_group(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, spw, e->variant_deep);
     if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev1, st);
     if (err == cudaSuccess) err = cudaMemcpyAsync(e->ing_digests_h, e->ing_digests, 32ull * n, cudaMemcpyDeviceToHost, st);
     if (err == cudaSuccess) err = cudaStreamSynchronize(st);

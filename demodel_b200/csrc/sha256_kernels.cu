@@ -37,100 +37,10 @@
 // /root/reference/cmd/demodel/start.go:201-204 returns resp unchanged).
 #include "sha256_kernels.cuh"
 #include "blobgen.h"
+#include "sha256_round.cuh"
 
 namespace dm {
 namespace {
-
-// ---------------------------------------------------------------------------
-// FIPS 180-4 §4.1.2 functions as single SASS ops.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t rotr(uint32_t x, uint32_t n) { return __funnelshift_r(x, x, n); }
-__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint32_t f_ch(uint32_t e, uint32_t f, uint32_t g)
-{
-    uint32_t d;   // (e & f) ^ (~e & g)
-    asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(e), "r"(f), "r"(g));
-    return d;
-}
-__device__ __forceinline__ uint32_t f_maj(uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t d;   // (a & b) ^ (a & c) ^ (b & c)
-    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint32_t big_sigma0(uint32_t x) { return xor3(rotr(x, 2), rotr(x, 13), rotr(x, 22)); }
-__device__ __forceinline__ uint32_t big_sigma1(uint32_t x) { return xor3(rotr(x, 6), rotr(x, 11), rotr(x, 25)); }
-__device__ __forceinline__ uint32_t small_sigma0(uint32_t x) { return xor3(rotr(x, 7), rotr(x, 18), x >> 3); }
-__device__ __forceinline__ uint32_t small_sigma1(uint32_t x) { return xor3(rotr(x, 17), rotr(x, 19), x >> 10); }
-__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
-
-// FIPS 180-4 §4.2.2.  Indexed only with compile-time constants inside fully
-// unrolled loops, so every use folds to an instruction immediate.
-#define DM_K256_TABLE                                                                        \
-    0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, \
-    0xab1c5ed5u, 0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, \
-    0x9bdc06a7u, 0xc19bf174u, 0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, \
-    0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau, 0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, \
-    0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u, 0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, \
-    0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u, 0xa2bfe8a1u, 0xa81a664bu, \
-    0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u, 0x19a4c116u, \
-    0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u, \
-    0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, \
-    0xc67178f2u
-
-// Runtime constants for FMA-pipe tricks (kernel argument; values fixed by the launcher).
-struct FmaK {
-    uint32_t one;                         // 1
-    uint32_t pad[3];
-};
-
-// Addition on the FMA pipe.  The integer ALU pipe (SHF/LOP3/IADD3) is the
-// bottleneck of SHA-256 on this part: ~84% of the round instructions can only
-// run there.  IMAD runs on the other (FMA) pipe, so `a*one + b` with a
-// *runtime* one (a kernel argument: ptxas cannot fold it back into IADD3)
-// moves the additions off the critical pipe.  kFma = 0 leaves the choice to
-// ptxas, 1 forces every round/schedule addition onto the FMA pipe with the
-// multiplier as a constant-bank operand, 2 does the same with the multiplier
-// held in a register (loaded from the job record).
-template <int kFma>
-__device__ __forceinline__ uint32_t addf(uint32_t a, uint32_t b, const FmaK &k)
-{
-    if constexpr (kFma == 0) {
-        return a + b;
-    } else {
-        uint32_t d;
-        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(k.one), "r"(b));
-        return d;
-    }
-}
-
-// One round, FIPS 180-4 §6.2.2 step 3, with the a..h rotation done by
-// renaming: v[] is indexed modulo 8 by the (compile-time) round number.
-//   T1 = h + S1(e) + Ch(e,f,g) + (K+W);  d += T1;  h = T1 + S0(a) + Maj(a,b,c)
-template <int kFma, int t>
-__device__ __forceinline__ void sha_round(uint32_t (&v)[8], uint32_t kw, const FmaK &k)
-{
-    constexpr int ia = (0 - t) & 7, ib = (1 - t) & 7, ic = (2 - t) & 7, id = (3 - t) & 7;
-    constexpr int ie = (4 - t) & 7, jf = (5 - t) & 7, ig = (6 - t) & 7, ih = (7 - t) & 7;
-    if constexpr (kFma == 0) {
-        const uint32_t t1 = v[ih] + big_sigma1(v[ie]) + f_ch(v[ie], v[jf], v[ig]) + kw;
-        const uint32_t t2 = big_sigma0(v[ia]) + f_maj(v[ia], v[ib], v[ic]);
-        v[id] += t1;
-        v[ih] = t1 + t2;
-    } else {
-        const uint32_t x = addf<1>(v[ih], kw, k);
-        const uint32_t y = addf<1>(x, f_ch(v[ie], v[jf], v[ig]), k);
-        const uint32_t t1 = addf<1>(y, big_sigma1(v[ie]), k);
-        const uint32_t t2 = addf<1>(big_sigma0(v[ia]), f_maj(v[ia], v[ib], v[ic]), k);
-        v[id] = addf<1>(v[id], t1, k);
-        v[ih] = addf<1>(t1, t2, k);
-    }
-}
 
 template <int kFma, int t0>
 __device__ __forceinline__ void sha_rounds4(uint32_t (&v)[8], const uint4 &k4, const FmaK &k)
@@ -665,7 +575,7 @@ __global__ void synth_fill_many_kernel(uint64_t seed, uint64_t first_blob, uint8
 
 }  // namespace
 
-static const FmaK kFmaK = {1u, {0u, 0u, 0u}};
+static const FmaK kFmaK = {1u, 0xffffffffu, {0u, 0u}};
 
 template <int kFma, int kStyle>
 static void launch_wide_t(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests, cudaStream_t stream)
@@ -698,26 +608,35 @@ cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *st
     switch (variant) {
     case 1: case 3: sha256_deep_kernel<1><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     case 2: sha256_deep_kernel<2><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 4: sha256_deep_kernel<4><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     default: sha256_deep_kernel<0><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     }
     return cudaGetLastError();
 }
 
-// streams_per_warp in {2, 4, 8, 16}
-cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests,
-                                cudaStream_t stream, int streams_per_warp)
+// streams_per_warp in {2, 4, 8, 16}; variant 4 = the short-chain round (see sha256_round.cuh), else ptxas' own
+template <int kFma>
+static cudaError_t launch_group_t(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests,
+                                  cudaStream_t stream, int streams_per_warp)
 {
-    if (njobs == 0) return cudaSuccess;
     const uint32_t spw = (uint32_t)streams_per_warp;
     const uint32_t grid = (njobs + spw - 1) / spw;
     switch (streams_per_warp) {
-    case 2: sha256_group_kernel<0, 2><<<grid, 32, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
-    case 4: sha256_group_kernel<0, 4><<<grid, 32, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
-    case 8: sha256_group_kernel<0, 8><<<grid, 32, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
-    case 16: sha256_group_kernel<0, 16><<<grid, 32, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 2: sha256_group_kernel<kFma, 2><<<grid, 32, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 4: sha256_group_kernel<kFma, 4><<<grid, 32, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 8: sha256_group_kernel<kFma, 8><<<grid, 32, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 16: sha256_group_kernel<kFma, 16><<<grid, 32, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests,
+                                cudaStream_t stream, int streams_per_warp, int variant)
+{
+    if (njobs == 0) return cudaSuccess;
+    return variant == 4 ? launch_group_t<4>(jobs, njobs, states, digests, stream, streams_per_warp)
+                        : launch_group_t<0>(jobs, njobs, states, digests, stream, streams_per_warp);
 }
 
 cudaError_t launch_synth_fill(uint64_t seed, uint64_t blob, uint64_t byte_off, void *dst, size_t len,

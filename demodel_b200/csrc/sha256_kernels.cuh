@@ -37,9 +37,10 @@ cudaError_t launch_sha256_wide(const HashJob *jobs, uint32_t njobs, uint32_t *st
 cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *states,
                                uint32_t *digests, cudaStream_t stream, int variant);
 constexpr int kDefaultWideVariant = 9;   // fma 1 + style 2
-// S streams per warp, S in {2,4,8,16}: the middle ground between deep and wide.
+// S streams per warp, S in {2,4,8,16}: the middle ground between deep and wide.  `variant` is the deep
+// kernel's (the serial phase is the same code): 4 = short-chain round, anything else = ptxas' ordering.
 cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *states,
-                                uint32_t *digests, cudaStream_t stream, int streams_per_warp);
+                                uint32_t *digests, cudaStream_t stream, int streams_per_warp, int variant);
 
 // Kernel choice by live-stream count: aim for one to two warps on
 // each of the 592 sub-partitions.  Returns streams per warp: 1 = deep, 32 = wide.

@@ -204,7 +204,7 @@ static cudaError_t run_all(const HashJob *jobs, uint32_t n, uint32_t *states, ui
 }
 cudaError_t launch_sha256_wide(const HashJob *j, uint32_t n, uint32_t *s, uint32_t *d, cudaStream_t st, int) { return run_all(j, n, s, d, st); }
 cudaError_t launch_sha256_deep(const HashJob *j, uint32_t n, uint32_t *s, uint32_t *d, cudaStream_t st, int) { return run_all(j, n, s, d, st); }
-cudaError_t launch_sha256_group(const HashJob *j, uint32_t n, uint32_t *s, uint32_t *d, cudaStream_t st, int) { return run_all(j, n, s, d, st); }
+cudaError_t launch_sha256_group(const HashJob *j, uint32_t n, uint32_t *s, uint32_t *d, cudaStream_t st, int, int) { return run_all(j, n, s, d, st); }
 
 cudaError_t launch_synth_fill(uint64_t seed, uint64_t blob, uint64_t off, void *dst, size_t len, cudaStream_t st)
 {

@@ -70,3 +70,14 @@ def test_engine_host_logic_soak_under_tsan_and_asan(tmp_path):
         assert build.returncode == 0, build.stderr[-3000:]
         out = subprocess.run([str(exe), "3", "6"], capture_output=True, text=True, timeout=300)
         assert out.returncode == 0 and "ENGINE SOAK OK" in out.stdout, (out.stdout + out.stderr)[-4000:]
+
+
+def test_every_round_form_is_sha256_on_the_host(tmp_path):
+    """sha256_round.cuh compiled as plain C++: each kernel round form (incl. the not-yet-default short chain)
+    must reproduce the oracle's digests - the operation ORDER is what the forms differ in."""
+    obj, exe = tmp_path / "oracle.o", tmp_path / "round_forms"
+    subprocess.run(["gcc", "-O2", "-c", os.path.join(ROOT, "oracle", "sha256_oracle.c"), "-o", str(obj)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-fsanitize=undefined", "-fno-sanitize-recover=undefined",
+                    os.path.join(ROOT, "tests", "native", "test_round_forms.cc"), str(obj), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ROUND FORMS OK" in out.stdout, out.stdout + out.stderr
