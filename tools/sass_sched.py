@@ -86,6 +86,9 @@ def decode(row):
     return dst, src, pipe
 
 
+WIDE_RT, WIDE_LAT = 2, 4      # IMAD.WIDE / IMAD.HI issue interval and latency: unmeasured, set by --wide-rt / --wide-lat
+
+
 def simulate(body, iters):
     ready = {}            # reg -> (cycle the value is available to a same-pipe consumer, producing pipe)
     pipe_free = {"alu": 0, "fma": 0, "lsu": 0, "other": 0}
@@ -99,12 +102,13 @@ def simulate(body, iters):
             for r in src:
                 if r in ready:
                     avail, ppipe, lat = ready[r]
-                    a = avail + (0 if (ppipe == pipe or lat > 5) else 1)
+                    a = avail + (0 if (ppipe == pipe or lat >= 29) else 1)
                     start = max(start, a)
-            lat = 29 if row[2] in ("LDS", "LDG", "LDC") else 4
+            wide = row[2] == "IMAD" and (".WIDE" in row[1] or ".HI" in row[1])
+            lat = 29 if row[2] in ("LDS", "LDG", "LDC") else WIDE_LAT if wide else 4
             for r in dst:
                 ready[r] = (start + lat, pipe, lat)
-            pipe_free[pipe] = start + 2
+            pipe_free[pipe] = start + (WIDE_RT if wide else 2)
             t = start + 1
         marks.append(t)
     return marks
@@ -116,7 +120,11 @@ def main():
     ap.add_argument("func")
     ap.add_argument("--iters", type=int, default=4)
     ap.add_argument("--rounds", type=int, default=64, help="rounds per loop iteration")
+    ap.add_argument("--wide-rt", type=int, default=2, help="assumed issue interval of IMAD.WIDE / IMAD.HI")
+    ap.add_argument("--wide-lat", type=int, default=4, help="assumed latency of IMAD.WIDE / IMAD.HI")
     a = ap.parse_args()
+    global WIDE_RT, WIDE_LAT
+    WIDE_RT, WIDE_LAT = a.wide_rt, a.wide_lat
     rows = parse(a.sass, a.func)
     if not rows:
         sys.exit("function not found")
