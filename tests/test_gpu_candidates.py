@@ -17,6 +17,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.xfail(strict=False, reason="candidate round ordering (deep variant 4): recorded, not gating, until measured")
 def test_short_chain_round_is_bit_exact_on_the_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_variant.py"), "9,4"],
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=240)
     print(out.stdout[-3000:])
     assert out.returncode == 0 and "VARIANT OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

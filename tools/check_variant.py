@@ -58,10 +58,11 @@ def run(variant):
         print(f"variant {variant} kernel {kernel!s:>5}: 1500 ragged blobs, {n_bad} mismatches")
         bad += n_bad
     # fused CAS copy: hash-and-cache, then read back
-    got, matched, _ = e.ingest_device(ddev.data_ptr(), off[:-1][:64], rs[:64], expect=b"".join(want[:64]), replace=True,
-                                      kernel="deep")
-    bad += sum(g != w for g, w in zip(got, want[:64])) + (0 if all(matched) else 1)
-    i = int(np.argmax(rs[:64]))
+    idx = [i for i in range(len(rs)) if rs[i] > 0][:64]
+    got, matched, _ = e.ingest_device(ddev.data_ptr(), [int(off[i]) for i in idx], [int(rs[i]) for i in idx],
+                                      expect=b"".join(want[i] for i in idx), replace=True, kernel="deep")
+    bad += sum(g != want[i] for g, i in zip(got, idx)) + (0 if all(matched) else 1)
+    i = max(idx, key=lambda j: rs[j])
     rid, sz = e.cache_open(want[i])
     back = e.cache_read(rid, 0, sz)
     e.cache_close(rid)
