@@ -322,6 +322,25 @@ sha256_wide_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
     store_state(s, states, digests, jb.slot, jb.flags);
 }
 
+// Phase 1 of the deep and group kernels: one lane expands the 64-entry schedule of its block and
+// stages W[t] + K[t] as 16 uint4 (FIPS 180-4 §6.2.2 step 1, K folded in).  Additions are left to ptxas:
+// forcing them onto the FMA pipe lengthens the w[t-2] -> w[t] chain and the timing model shows no gain.
+__device__ __forceinline__ void expand_schedule(uint32_t (&w)[16], uint4 *out)
+{
+    constexpr uint32_t K[64] = {DM_K256_TABLE};
+#pragma unroll
+    for (int t = 0; t < 16; t += 4)
+        out[t >> 2] = make_uint4(w[t] + K[t], w[t + 1] + K[t + 1], w[t + 2] + K[t + 2], w[t + 3] + K[t + 3]);
+#pragma unroll
+    for (int t = 16; t < 64; t += 4) {
+#pragma unroll
+        for (int u = t; u < t + 4; ++u)
+            w[u & 15] += small_sigma1(w[(u - 2) & 15]) + w[(u - 7) & 15] + small_sigma0(w[(u - 15) & 15]);
+        out[t >> 2] = make_uint4(w[t & 15] + K[t], w[(t + 1) & 15] + K[t + 1],
+                                 w[(t + 2) & 15] + K[t + 2], w[(t + 3) & 15] + K[t + 3]);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // deep: one warp per stream
 // ---------------------------------------------------------------------------
@@ -335,7 +354,6 @@ sha256_deep_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
                    uint32_t *__restrict__ digests, FmaK k)
 {
     __shared__ __align__(16) uint32_t kw_smem[kDeepWarps][32 * kKwStride];
-    constexpr uint32_t K[64] = {DM_K256_TABLE};
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t wid = threadIdx.x >> 5;
     const uint32_t j = blockIdx.x * kDeepWarps + wid;
@@ -370,17 +388,7 @@ sha256_deep_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
             uint32_t w[16];
             unpack_be(w, x[0], x[1], x[2], x[3]);
             uint4 *out = reinterpret_cast<uint4 *>(kw + lane * kKwStride);
-#pragma unroll
-            for (int t = 0; t < 16; t += 4)
-                out[t >> 2] = make_uint4(w[t] + K[t], w[t + 1] + K[t + 1], w[t + 2] + K[t + 2], w[t + 3] + K[t + 3]);
-#pragma unroll
-            for (int t = 16; t < 64; t += 4) {
-#pragma unroll
-                for (int u = t; u < t + 4; ++u)
-                    w[u & 15] += small_sigma1(w[(u - 2) & 15]) + w[(u - 7) & 15] + small_sigma0(w[(u - 15) & 15]);
-                out[t >> 2] = make_uint4(w[t & 15] + K[t], w[(t + 1) & 15] + K[t + 1],
-                                         w[(t + 2) & 15] + K[t + 2], w[(t + 3) & 15] + K[t + 3]);
-            }
+            expand_schedule(w, out);
         }
         __syncwarp();
         // prefetch the next group's block while the serial rounds run
@@ -434,7 +442,6 @@ sha256_group_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *
 {
     constexpr uint32_t B = 32 / S;
     __shared__ __align__(16) uint32_t kw[32 * kKwStride];
-    constexpr uint32_t K[64] = {DM_K256_TABLE};
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t j = lane % S, b = lane / S;
     const uint32_t job = blockIdx.x * S + j;
@@ -474,17 +481,7 @@ sha256_group_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *
             uint32_t w[16];
             unpack_be(w, x[0], x[1], x[2], x[3]);
             uint4 *out = reinterpret_cast<uint4 *>(kw + lane * kKwStride);
-#pragma unroll
-            for (int t = 0; t < 16; t += 4)
-                out[t >> 2] = make_uint4(w[t] + K[t], w[t + 1] + K[t + 1], w[t + 2] + K[t + 2], w[t + 3] + K[t + 3]);
-#pragma unroll
-            for (int t = 16; t < 64; t += 4) {
-#pragma unroll
-                for (int u = t; u < t + 4; ++u)
-                    w[u & 15] += small_sigma1(w[(u - 2) & 15]) + w[(u - 7) & 15] + small_sigma0(w[(u - 15) & 15]);
-                out[t >> 2] = make_uint4(w[t & 15] + K[t], w[(t + 1) & 15] + K[t + 1],
-                                         w[(t + 2) & 15] + K[t + 2], w[(t + 3) & 15] + K[t + 3]);
-            }
+            expand_schedule(w, out);
         }
         __syncwarp();
         p += 4 * B; q += 4 * B;
