@@ -5,6 +5,7 @@
 #include "../../demodel_b200/csrc/sha256_kernels.cuh"
 #include "../../demodel_b200/csrc/blobgen.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -20,6 +21,7 @@ extern "C" {
 #include <condition_variable>
 #include <deque>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -94,14 +96,59 @@ cudaError_t cudaDeviceSynchronize(void)
 cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = 1ull << 30; return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t) { return "fake cuda error"; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
-cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
-cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = calloc(1, n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
-cudaError_t cudaHostGetDevicePointer(void **dev, void *host, unsigned) { *dev = host; return cudaSuccess; }
-cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t st)
+// Allocation registries: an asynchronous copy whose host side is not pinned is a bug in the caller even
+// though real CUDA accepts it - the call may return before the bytes have been read (H2D) or written (D2H),
+// which is how the resume-state upload once raced with the first job.  The fake refuses it loudly.
+static std::mutex g_alloc_mu;
+static std::map<uintptr_t, size_t> g_pinned, g_device;
+static void reg_add(std::map<uintptr_t, size_t> &m, void *p, size_t n) { std::lock_guard<std::mutex> g(g_alloc_mu); m[(uintptr_t)p] = n ? n : 1; }
+static void reg_del(std::map<uintptr_t, size_t> &m, void *p) { std::lock_guard<std::mutex> g(g_alloc_mu); m.erase((uintptr_t)p); }
+static bool reg_has(std::map<uintptr_t, size_t> &m, const void *p, size_t n)
 {
+    std::lock_guard<std::mutex> g(g_alloc_mu);
+    auto it = m.upper_bound((uintptr_t)p);
+    if (it == m.begin()) return false;
+    --it;
+    return (uintptr_t)p + n <= it->first + it->second;
+}
+[[noreturn]] static void misuse(const char *what)
+{
+    fprintf(stderr, "FAKE CUDA: %s\n", what);
+    abort();
+}
+
+cudaError_t cudaMalloc(void **p, size_t n)
+{
+    *p = malloc(n ? n : 1);
+    if (!*p) return cudaErrorMemoryAllocation;
+    reg_add(g_device, *p, n);
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void *p) { if (p) reg_del(g_device, p); free(p); return cudaSuccess; }
+cudaError_t cudaHostAlloc(void **p, size_t n, unsigned)
+{
+    *p = calloc(1, n ? n : 1);
+    if (!*p) return cudaErrorMemoryAllocation;
+    reg_add(g_pinned, *p, n);
+    return cudaSuccess;
+}
+cudaError_t cudaFreeHost(void *p) { if (p) reg_del(g_pinned, p); free(p); return cudaSuccess; }
+cudaError_t cudaHostGetDevicePointer(void **dev, void *host, unsigned)
+{
+    if (!reg_has(g_pinned, host, 1)) misuse("cudaHostGetDevicePointer on memory that is not pinned");
+    *dev = host;
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind kind, cudaStream_t st)
+{
+    if (n) {
+        const bool d_dev = reg_has(g_device, d, n), s_dev = reg_has(g_device, s, n);
+        const bool d_pin = reg_has(g_pinned, d, n), s_pin = reg_has(g_pinned, s, n);
+        if (kind == cudaMemcpyHostToDevice && !(s_pin && (d_dev || d_pin))) misuse("cudaMemcpyAsync H2D: source not pinned or destination not device memory");
+        if (kind == cudaMemcpyDeviceToHost && !((s_dev || s_pin) && d_pin)) misuse("cudaMemcpyAsync D2H: destination not pinned or source not device memory");
+        if (kind == cudaMemcpyDeviceToDevice && !(s_dev && d_dev)) misuse("cudaMemcpyAsync D2D: not device memory on both sides");
+    }
     on_stream(st, [d, s, n] { memcpy(d, s, n); });
     return cudaSuccess;
 }
