@@ -262,7 +262,7 @@ struct dm_engine {
     std::condition_variable work_cv;
     std::vector<std::shared_ptr<Stream>> dirty;
     std::vector<Slab *> pending_slabs;
-    bool stop = false;
+    std::atomic<bool> stop{false};   // set under work_mu; the spill threads read it under spill_mu
     std::thread pump;
     Cycle cycles[kCycles];
     SlabBatch batches[kSlabBatches];
@@ -2101,7 +2101,6 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
     if (flags & DM_ING_FORCE_WIDE) spw = 32;
     if (flags & DM_ING_FORCE_DEEP) spw = 1;
     if (flags & DM_ING_SPW_MASK) spw = 1 << (((flags & DM_ING_SPW_MASK) >> DM_ING_SPW_SHIFT) - 1);
-    const bool deep = spw == 1;
     std::vector<uint32_t> order(n);
     for (uint32_t i = 0; i < n; ++i) order[i] = i;
     if (spw > 1) {

@@ -65,7 +65,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
         uint8_t got[32];
         int matched = -1, rc;
         uint64_t id = 0;
-        const int op = (int)(rng() % 12);
+        const int op = (int)(rng() % 14);
         ops++;
         if (op <= 1) {                                               // sequential, random piece size
             rc = dm_stream_open(e, b.digest, (rng() & 1) ? n : 0, &id);
@@ -203,6 +203,81 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
             if (rc == 1) continue;
             CHECK(rc == DM_OK);
             CHECK(matched == 1 && memcmp(got, b.digest, 32) == 0);
+        } else if (op == 12 && !verify_only) {                       // a ragged batch already "in HBM": one launch
+            const uint32_t nb = 1 + (uint32_t)(rng() % 24);
+            std::vector<uint64_t> off(nb), len(nb);
+            uint64_t pos = 0;
+            for (uint32_t i = 0; i < nb; ++i) {
+                off[i] = pos;
+                len[i] = (rng() % 6 == 0) ? 0 : 16 * (rng() % 3000) + (rng() % 3 == 0 ? rng() % 16 : 0);
+                pos += (len[i] + 15) / 16 * 16;
+            }
+            std::vector<uint8_t> dev(pos + 16);                      // the rig's device memory is host memory
+            const uint64_t first = 9000 + rng() % 100000;
+            CHECK(dm_synth_fill_device_many(e, 0xDE40DE1, first, dev.data(), off.data(), len.data(), nb) == DM_OK);
+            std::vector<uint8_t> want(32 * nb), digs(32 * nb), mat(nb, 7);
+            for (uint32_t i = 0; i < nb; ++i) dmo_sha256(dev.data() + off[i], len[i], &want[32 * i]);
+            {   // the device generator must equal the host generator
+                const uint32_t i = (uint32_t)(rng() % nb);
+                std::vector<uint8_t> host(len[i]);
+                dm_synth_fill_host(0xDE40DE1, first + i, 0, host.data(), len[i]);
+                CHECK(len[i] == 0 || memcmp(host.data(), dev.data() + off[i], len[i]) == 0);
+            }
+            const bool cache = rng() & 1;
+            std::vector<uint8_t> expect = want;
+            const uint32_t ci = (uint32_t)(rng() % nb);
+            const bool corrupt = rng() % 4 == 0;
+            if (corrupt) expect[32 * ci] ^= 1;
+            uint32_t flags = cache ? DM_ING_REPLACE : DM_ING_HASH_ONLY;
+            const uint32_t pick = (uint32_t)(rng() % 8);
+            if (pick >= 1 && pick <= 6) flags |= pick << DM_ING_SPW_SHIFT;      // 1, 2, 4, 8, 16, 32 streams per warp
+            double ms = -1;
+            rc = dm_ingest_device(e, dev.data(), off.data(), len.data(), nb, expect.data(), digs.data(), mat.data(), flags, &ms);
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
+            CHECK(memcmp(digs.data(), want.data(), 32 * nb) == 0);
+            for (uint32_t i = 0; i < nb; ++i) {
+                const bool same_as_ci = memcmp(&want[32 * i], &want[32 * ci], 32) == 0;   // duplicates (empty blobs) share the verdict
+                if (!(corrupt && same_as_ci)) CHECK(mat[i] == 1);
+                if (corrupt && i == ci) CHECK(mat[i] == 0);
+            }
+            if (cache) {
+                const uint32_t i = (uint32_t)(rng() % nb);
+                uint64_t rid = 0, size = 0;
+                if (!(corrupt && i == ci) && dm_cache_open(e, &want[32 * i], &rid, &size) == DM_OK) {
+                    CHECK(size == len[i]);
+                    void *ptrs[16];
+                    uint64_t lens[16];
+                    const int ne = dm_cache_device_extents(e, rid, ptrs, lens, 16);
+                    CHECK((ne >= 0 && ne <= 16) || ne == DM_ESTATE);       // DM_ESTATE: already evicted to the disk tier
+                    uint64_t seen = ne < 0 ? size : 0;
+                    for (int x = 0; x < ne; ++x) {                   // in the rig a device pointer can be read directly
+                        CHECK(memcmp(ptrs[x], dev.data() + off[i] + seen, lens[x]) == 0);
+                        seen += lens[x];
+                    }
+                    CHECK(seen == size);
+                    CHECK(dm_cache_close(e, rid) == DM_OK);
+                }
+            }
+        } else if (op == 13) {                                       // response headers travel with the blob
+            rc = dm_stream_open(e, b.digest, n, &id);
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
+            CHECK(dm_stream_set_meta(e, id, "Content-Type", "application/octet-stream") == DM_OK);
+            CHECK(dm_stream_set_meta(e, id, "ETag", "\"quoted\\value\"") == DM_OK);
+            rc = dm_stream_write(e, id, p, n);
+            if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); continue; }
+            rc = finish_or_skip(e, id, false, got, &matched);
+            if (rc == 1) continue;
+            CHECK(rc == DM_OK && matched == 1);
+            uint64_t rid = 0, size = 0;
+            if (!verify_only && dm_cache_open(e, b.digest, &rid, &size) == DM_OK) {
+                char meta[1024];
+                size_t mlen = 0;
+                CHECK(dm_cache_meta(e, rid, meta, sizeof meta, &mlen) == DM_OK && mlen < sizeof meta);
+                CHECK(strstr(meta, "\"digest\":\"sha256:") != nullptr);
+                CHECK(dm_cache_close(e, rid) == DM_OK);
+            }
         } else if (op == 11) {                                       // metadata + stats are always safe to call
             dm_stats st;
             CHECK(dm_engine_stats(e, &st) == DM_OK);

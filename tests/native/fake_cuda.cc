@@ -18,6 +18,7 @@ extern "C" {
 // than the call that enqueued them, so ThreadSanitizer sees any host-side reuse of a buffer that is not
 // ordered after the event guarding it as a data race — exactly the engine's lifetime rules.
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -27,11 +28,20 @@ extern "C" {
 #include <thread>
 #include <vector>
 
+// FAKE_CUDA_JITTER_US=n: every queued operation starts after a random 0..n us pause, so that the windows
+// between "enqueued" and "executed" that real hardware has (and a fast CPU thread hides) are explored.
+static unsigned jitter_us()
+{
+    static const unsigned j = [] { const char *v = getenv("FAKE_CUDA_JITTER_US"); return v ? (unsigned)atoi(v) : 0u; }();
+    return j;
+}
+
 struct fakeStream {
     std::mutex mu;
     std::condition_variable cv;
     std::deque<std::function<void()>> q;
     bool stop = false, busy = false;
+    uint64_t rng = (uint64_t)(uintptr_t)this;
     std::thread th;
     fakeStream() : th([this] { run(); }) {}
     void run()
@@ -45,6 +55,10 @@ struct fakeStream {
                 f = std::move(q.front());
                 q.pop_front();
                 busy = true;
+            }
+            if (const unsigned j = jitter_us()) {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                std::this_thread::sleep_for(std::chrono::microseconds((rng >> 33) % (j + 1)));
             }
             f();
             {
@@ -96,9 +110,14 @@ cudaError_t cudaDeviceSynchronize(void)
 cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = 1ull << 30; return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t) { return "fake cuda error"; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
-// Allocation registries: an asynchronous copy whose host side is not pinned is a bug in the caller even
-// though real CUDA accepts it - the call may return before the bytes have been read (H2D) or written (D2H),
-// which is how the resume-state upload once raced with the first job.  The fake refuses it loudly.
+// Allocation registries, to model what the real runtime does with PAGEABLE host memory:
+//   cudaMemcpyAsync H2D  - the source is staged before the call returns (snapshot here), the device write is
+//                          stream-ordered;
+//   cudaMemcpyAsync D2H  - synchronous with respect to the host (enqueue, then wait);
+//   cudaMemcpy      H2D  - returns after staging; the device write completes LATER and is not ordered with
+//                          work on non-blocking streams (deferred on a hidden legacy stream here) - which is
+//                          how the resume-state upload once raced with the first job.
+// With pinned memory the copy touches the caller's buffer on the stream thread, so TSan sees reuse races.
 static std::mutex g_alloc_mu;
 static std::map<uintptr_t, size_t> g_pinned, g_device;
 static void reg_add(std::map<uintptr_t, size_t> &m, void *p, size_t n) { std::lock_guard<std::mutex> g(g_alloc_mu); m[(uintptr_t)p] = n ? n : 1; }
@@ -139,17 +158,32 @@ cudaError_t cudaHostGetDevicePointer(void **dev, void *host, unsigned)
     *dev = host;
     return cudaSuccess;
 }
-cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
+static fakeStream *legacy_stream()
+{
+    static fakeStream *ls = [] { auto *x = new fakeStream(); std::lock_guard<std::mutex> g(g_reg_mu); g_streams.push_back(x); return x; }();
+    return ls;
+}
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind kind)
+{
+    if (kind == cudaMemcpyHostToDevice && n && !reg_has(g_pinned, s, n)) {
+        auto snap = std::make_shared<std::vector<uint8_t>>((const uint8_t *)s, (const uint8_t *)s + n);
+        legacy_stream()->push([d, snap] { memcpy(d, snap->data(), snap->size()); });
+        return cudaSuccess;
+    }
+    cudaDeviceSynchronize();
+    memcpy(d, s, n);
+    return cudaSuccess;
+}
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind kind, cudaStream_t st)
 {
-    if (n) {
-        const bool d_dev = reg_has(g_device, d, n), s_dev = reg_has(g_device, s, n);
-        const bool d_pin = reg_has(g_pinned, d, n), s_pin = reg_has(g_pinned, s, n);
-        if (kind == cudaMemcpyHostToDevice && !(s_pin && (d_dev || d_pin))) misuse("cudaMemcpyAsync H2D: source not pinned or destination not device memory");
-        if (kind == cudaMemcpyDeviceToHost && !((s_dev || s_pin) && d_pin)) misuse("cudaMemcpyAsync D2H: destination not pinned or source not device memory");
-        if (kind == cudaMemcpyDeviceToDevice && !(s_dev && d_dev)) misuse("cudaMemcpyAsync D2D: not device memory on both sides");
+    if (n == 0) return cudaSuccess;
+    if (kind == cudaMemcpyHostToDevice && !reg_has(g_pinned, s, n)) {
+        auto snap = std::make_shared<std::vector<uint8_t>>((const uint8_t *)s, (const uint8_t *)s + n);
+        on_stream(st, [d, snap] { memcpy(d, snap->data(), snap->size()); });
+        return cudaSuccess;
     }
     on_stream(st, [d, s, n] { memcpy(d, s, n); });
+    if (kind == cudaMemcpyDeviceToHost && !reg_has(g_pinned, d, n) && st) st->drain();
     return cudaSuccess;
 }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned)

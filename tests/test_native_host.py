@@ -41,9 +41,11 @@ def _build_rig(exe, *flags):
 
 
 def test_engine_host_logic_soak_under_tsan_and_asan(tmp_path):
-    """The whole engine (engine.cu + proxy driver + manifest) compiled with plain g++ against a fake,
-    synchronous CUDA runtime whose SHA-256 'kernels' are the CPU oracle (tests/native/fake_cuda*: test
-    infrastructure, never part of the product), then soaked through the C-ABI by 6 threads mixing every
+    """The whole engine (engine.cu + proxy driver + manifest) compiled with plain g++ against a fake CUDA
+    runtime that is asynchronous like the real one (a worker thread per stream; copies and 'kernels' - the
+    CPU oracle - run there; tests/native/fake_cuda*: test infrastructure, never part of the product), so
+    that touching a slab, extent or job table before the event guarding it is a data race TSan reports;
+    then soaked through the C-ABI by 6 threads mixing every
     ingest form, aborts, mismatches, cache reads, followers, evictions, checkpoint/resume — under
     ThreadSanitizer and under ASan+UBSan, with a tiny arena and ring so eviction and back-pressure are
     constantly exercised, in HBM-tier, disk-tier and verify-only modes.  No GPU involved: this is the
@@ -58,7 +60,10 @@ def test_engine_host_logic_soak_under_tsan_and_asan(tmp_path):
                 continue                                          # this toolchain lacks that sanitizer runtime
             raise AssertionError(build.stderr[-3000:])
         env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66", ASAN_OPTIONS="detect_leaks=0")
-        for mode in (["3", "6"], ["3", "6", str(tmp_path / f"cas_{name}")], ["3", "6", "", "1"]):
+        # the last run delays every queued operation by a random 0..300 us: real hardware's enqueue-to-execute gap
+        for mode, jitter in ((["3", "6"], "0"), (["3", "6", str(tmp_path / f"cas_{name}")], "0"), (["3", "6", "", "1"], "0"),
+                             (["3", "6"], "300")):
+            env["FAKE_CUDA_JITTER_US"] = jitter
             out = subprocess.run([str(exe), *mode], capture_output=True, text=True, timeout=300, env=env)
             text = out.stdout + out.stderr
             assert out.returncode == 0 and "ENGINE SOAK OK" in out.stdout, text[-4000:]
