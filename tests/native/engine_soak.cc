@@ -65,7 +65,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
         uint8_t got[32];
         int matched = -1, rc;
         uint64_t id = 0;
-        const int op = (int)(rng() % 14);
+        const int op = (int)(rng() % 15);
         ops++;
         if (op <= 1) {                                               // sequential, random piece size
             rc = dm_stream_open(e, b.digest, (rng() & 1) ? n : 0, &id);
@@ -277,6 +277,59 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
                 CHECK(dm_cache_meta(e, rid, meta, sizeof meta, &mlen) == DM_OK && mlen < sizeof meta);
                 CHECK(strstr(meta, "\"digest\":\"sha256:") != nullptr);
                 CHECK(dm_cache_close(e, rid) == DM_OK);
+            }
+        } else if (op == 14) {                                       // API abuse: errors, never a crash or a leak
+            const uint64_t bogus = 0x7000000000ull + rng() % 1000;
+            size_t nread = 0, cap = 0;
+            void *win = nullptr;
+            CHECK(dm_stream_write(e, bogus, scratch.data(), 1) < 0);
+            CHECK(dm_stream_write_at(e, bogus, 0, scratch.data(), 1) < 0);
+            CHECK(dm_stream_finish(e, bogus, got, &matched) < 0);
+            CHECK(dm_stream_flush(e, bogus) < 0);
+            CHECK(dm_stream_abort(e, bogus) < 0);
+            CHECK(dm_stream_acquire(e, bogus, &win, &cap) < 0);
+            CHECK(dm_stream_commit(e, bogus, 1) < 0);
+            CHECK(dm_stream_set_meta(e, bogus, "k", "v") < 0);
+            CHECK(dm_cache_read(e, bogus, 0, scratch.data(), 10, &nread) < 0);
+            CHECK(dm_cache_close(e, bogus) < 0);
+            CHECK(dm_stream_open(nullptr, b.digest, n, &id) < 0);
+            CHECK(dm_stream_open(e, b.digest, n, nullptr) < 0);
+            CHECK(dm_cache_open(e, nullptr, &id, nullptr) < 0);
+            dm_checkpoint junk;
+            memset(&junk, 0xee, sizeof junk);
+            CHECK(dm_stream_resume(e, &junk, b.digest, n, &id) < 0);
+            rc = dm_stream_open(e, nullptr, 0, &id);                 // unknown size, no expectation
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
+            rc = dm_stream_acquire(e, id, &win, &cap);
+            if (rc == DM_OK) {
+                CHECK(cap > 0);
+                CHECK(dm_stream_acquire(e, id, &win, &cap) == DM_ESTATE);       // one window at a time
+                CHECK(dm_stream_write(e, id, scratch.data(), 1) == DM_ESTATE);
+                CHECK(dm_stream_commit(e, id, cap + 1) == DM_EINVAL);
+                CHECK(dm_stream_commit(e, id, 0) == DM_OK);
+                CHECK(dm_stream_commit(e, id, 0) == DM_ESTATE);
+            } else {
+                CHECK(tolerate(rc));
+            }
+            if (n) { rc = dm_stream_write(e, id, p, std::min<size_t>(n, 5000)); CHECK(rc == DM_OK || tolerate(rc)); }
+            if (rc != DM_OK) { dm_stream_abort(e, id); continue; }
+            rc = finish_or_skip(e, id, false, got, &matched);
+            if (rc == 1) continue;
+            CHECK(rc == DM_OK && matched == 1);                      // no expectation: whatever arrived is accepted
+            CHECK(dm_stream_finish(e, id, got, &matched) < 0);       // finish released the id
+            CHECK(dm_stream_write(e, id, scratch.data(), 1) < 0);
+            CHECK(dm_stream_abort(e, id) < 0);
+            uint64_t rid = 0, size = 0;
+            if (!verify_only && dm_cache_open(e, got, &rid, &size) == DM_OK) {
+                CHECK(size == std::min<size_t>(n, 5000));
+                CHECK(dm_cache_read(e, rid, size + 1, scratch.data(), 1, &nread) == DM_ERANGE);
+                CHECK(dm_cache_read(e, rid, size, scratch.data(), 1, &nread) == DM_OK && nread == 0);      // EOF
+                rc = dm_cache_evict(e, got);
+                CHECK(rc == DM_ESTATE || rc == DM_ENOENT || rc == DM_OK);        // busy here; another thread may hold or have evicted it
+                CHECK(dm_cache_close(e, rid) == DM_OK);
+                CHECK(dm_cache_close(e, rid) < 0);
+                CHECK(dm_cache_read(e, rid, 0, scratch.data(), 1, &nread) < 0);
             }
         } else if (op == 11) {                                       // metadata + stats are always safe to call
             dm_stats st;
