@@ -78,6 +78,23 @@ def _kernel_for(n):
     return "wide (32 streams/warp)"
 
 
+def _int_issue_roofline(n_streams, hashed_gbs, sm_mhz):
+    """The bound that actually binds SHA-256 on sm_100a (profiles/r01_ubench_issue_rates.txt):
+    the ALU pipe takes one warp-instruction per 2 cycles per sub-partition.  Chip ceiling: >= 1040 ALU-pipe
+    instructions per 64-byte block per warp of 32 lanes on 592 sub-partitions.  Few streams: one warp per
+    stream needs >= 12 ALU-pipe instructions = 24 cycles per round, 64 rounds per 64 bytes.  Reported beside the
+    HBM roofline the metric asks for; never raises."""
+    try:
+        ghz = (sm_mhz or 1965.0) / 1e3
+        chip = 592 * ghz * (32 * 64) / (1040 * 2)                 # GB/s
+        per_stream = ghz / 24.0                                    # GB/s: 1 byte per round
+        peak = min(chip, n_streams * per_stream)
+        return {"bound": "int32 ALU-pipe issue", "peak": peak, "achieved": hashed_gbs, "frac": hashed_gbs / peak, "unit": "GB/s hashed",
+                "chip_ceiling": chip, "per_stream_ceiling": per_stream, "streams": n_streams, "sm_ghz": ghz}
+    except Exception as ex:                                        # reporting only
+        return {"error": repr(ex)}
+
+
 def _numa_bind(local_rank):
     """Opt-in (--numa-bind): pin this process (and every thread it creates later: pump, spill, connection
     workers) to the CPUs of the NUMA node its GPU hangs off, so the pinned ring and the host buffers are
@@ -520,7 +537,8 @@ def main():
                        "parallelism": f"shard{world} (URL-hash homed, no collective)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_blob_byte": bytes_per_blob_byte, "kernel_ms_per_step": kernel_ms_max / args.steps},
+                         "algorithmic_bytes_per_blob_byte": bytes_per_blob_byte, "kernel_ms_per_step": kernel_ms_max / args.steps,
+                         "int_issue": _int_issue_roofline(n, achieved / bytes_per_blob_byte, (clocks or {}).get("sm_mhz"))},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "probes": probes,
             "notes": {
                 "workload_choice": "BASELINE configs[2] (256 x 64 MiB, 17.18 GB) is the largest single-GPU configuration; "
