@@ -163,6 +163,11 @@ struct Stream {
     // retained.  Slabs are DMA'd to the device mirror of the ring and hashed from there, one slab per
     // job in arrival order; a slab returns to the ring when its job has run.
     bool verify_only = false;
+    // A verify-only stream whose partly filled slab is recalled by ring back-pressure keeps the bytes past
+    // the last whole block here (jobs hash whole blocks); they lead the stream's next slab.  carry_fill > 0
+    // implies cur == nullptr.
+    uint8_t carry[64];
+    uint32_t carry_fill = 0;
     std::deque<std::pair<Slab *, uint32_t>> staged;
     std::vector<std::pair<std::string, std::string>> meta;   // dm_stream_set_meta
     uint32_t followers = 0;    // readers attached while the body is still arriving (request coalescing)
@@ -263,6 +268,7 @@ struct dm_engine {
     std::vector<std::shared_ptr<Stream>> dirty;
     std::vector<Slab *> pending_slabs;
     std::atomic<bool> stop{false};   // set under work_mu; the spill threads read it under spill_mu
+    std::atomic<int> ring_waiters{0};   // writers blocked in slab_get(): the pump keeps recalling partial slabs meanwhile
     std::thread pump;
     Cycle cycles[kCycles];
     SlabBatch batches[kSlabBatches];
@@ -412,7 +418,9 @@ Slab *slab_get(dm_engine *e)
         { std::lock_guard<std::mutex> gw(e->work_mu); e->ring_starved.store(true); }   // under the pump's mutex: no lost wake-up
         e->work_cv.notify_one();
     }
+    e->ring_waiters++;
     e->slab_cv.wait(g, [&] { return !e->slab_free.empty() || e->stop; });
+    e->ring_waiters--;
     if (e->slab_free.empty()) return nullptr;
     Slab *s = e->slab_free.back();
     e->slab_free.pop_back();
@@ -440,7 +448,8 @@ int take_slab(dm_engine *e, Stream *s, std::unique_lock<std::mutex> &g)
     if (s->st != St::Open) { slab_put(e, fresh); return fail(DM_ESTATE, "stream closed while waiting for the ring"); }
     if (s->cur) { slab_put(e, fresh); return DM_OK; }
     s->cur = fresh;
-    s->cur_fill = 0;
+    s->cur_fill = s->carry_fill;
+    if (s->carry_fill) { memcpy(fresh->host, s->carry, s->carry_fill); s->carry_fill = 0; }
     return DM_OK;
 }
 
@@ -872,8 +881,9 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
     return true;
 }
 
-// Ring back-pressure relief (pump thread): DMA the partly filled sequential slabs of open streams so
-// they return to the ring.  try_lock only — a stream busy in a write keeps its slab this round.
+// Ring back-pressure relief (pump thread): DMA the partly filled slabs of open streams - the sequential
+// one and those of range parts (a client fetching one blob as P parallel ranges holds P of them) - so
+// they return to the ring.  try_lock only: a stream busy in a write keeps its slabs this round.
 void flush_partial_slabs(dm_engine *e)
 {
     std::vector<std::shared_ptr<Stream>> all;
@@ -884,8 +894,17 @@ void flush_partial_slabs(dm_engine *e)
     for (auto &sp : all) {
         Stream *s = sp.get();
         std::unique_lock<std::mutex> g(s->mu, std::try_to_lock);
-        if (!g.owns_lock() || s->st != St::Open || s->window_out || !s->cur || s->cur_fill == 0) continue;
-        if (s->verify_only && (s->cur_fill & 63)) continue;      // slab-by-slab hashing needs whole blocks
+        if (!g.owns_lock() || s->st != St::Open || s->window_out) continue;
+        // a part that was sent early simply becomes an island; the range continues in a fresh part
+        for (size_t i = s->parts.size(); i-- > 0;)
+            if (s->parts[i].fill) submit_part(e, sp, i);
+        if (!s->cur || s->cur_fill == 0) continue;
+        if (s->verify_only && (s->cur_fill & 63)) {              // slab-by-slab hashing needs whole blocks:
+            const uint32_t whole = s->cur_fill & ~63u;           // send those, keep the tail in the stream
+            s->carry_fill = s->cur_fill - whole;
+            memcpy(s->carry, s->cur->host + whole, s->carry_fill);
+            s->cur_fill = whole;                                 // (0 whole blocks: submit_slab just returns the slab)
+        }
         submit_slab(e, sp);
     }
 }
@@ -904,6 +923,7 @@ void pump_main(dm_engine *e)
     int b_head = 0, b_tail = 0, b_live = 0;
     std::vector<std::shared_ptr<Stream>> ready, inbox;
     std::vector<Slab *> slabs;
+    int starve_ticks = 0;
     bool retry_ready = false;       // ready streams blocked only by their own in-flight job
     bool launched = false;
     for (;;) {
@@ -917,7 +937,11 @@ void pump_main(dm_engine *e)
             b.slabs.clear(); b.busy = false;
             b_tail = (b_tail + 1) % kSlabBatches; --b_live;
         }
-        if (e->ring_starved.exchange(false)) flush_partial_slabs(e);
+        // a recall can miss slabs (stream busy in a write, window lent out): repeat while writers wait
+        if (e->ring_starved.exchange(false) || (e->ring_waiters.load() > 0 && ++starve_ticks >= 16)) {
+            starve_ticks = 0;
+            flush_partial_slabs(e);
+        }
         // 2. finished hash launches (any order)
         bool reaped = false;
         for (Cycle &c : e->cycles)
@@ -928,7 +952,8 @@ void pump_main(dm_engine *e)
             std::unique_lock<std::mutex> g(e->work_mu);
             const bool idle = !n_inflight && !b_live && ready.empty() && slabs.empty();
             if (e->dirty.empty() && e->pending_slabs.empty() && !e->stop && !launched && !reaped) {
-                if (idle) e->work_cv.wait(g, [&] { return !e->dirty.empty() || !e->pending_slabs.empty() || e->stop || e->ring_starved.load(); });
+                if (idle && e->ring_waiters.load() == 0)
+                    e->work_cv.wait(g, [&] { return !e->dirty.empty() || !e->pending_slabs.empty() || e->stop || e->ring_starved.load(); });
                 else e->work_cv.wait_for(g, std::chrono::microseconds(40));
             }
             stopping = e->stop;
@@ -1439,7 +1464,7 @@ int dm_stream_write_at(dm_engine *e, uint64_t id, uint64_t offset, const void *b
     Stream *s = sp.get();
     std::unique_lock<std::mutex> g(s->mu);
     if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open for write");
-    if (offset == s->dma_issued + s->cur_fill && s->parts.empty() && s->islands.empty()) {
+    if (offset == s->dma_issued + s->cur_fill + s->carry_fill && s->parts.empty() && s->islands.empty()) {
         g.unlock();
         return dm_stream_write(e, id, buf, len);          // plain sequential continuation
     }
@@ -1602,12 +1627,18 @@ int dm_stream_commit(dm_engine *e, uint64_t id, size_t len)
 }
 
 // Flush the partial slab and hand the stream to the pump for its final job.  Stream mutex held.
-static int begin_finish(dm_engine *e, const std::shared_ptr<Stream> &sp)
+static int begin_finish(dm_engine *e, const std::shared_ptr<Stream> &sp, std::unique_lock<std::mutex> &g)
 {
     Stream *s = sp.get();
     if (s->st == St::Finishing || s->st == St::Done) return DM_OK;
     if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open");
-    int rc = submit_slab(e, sp);
+    int rc = DM_OK;
+    if (s->carry_fill && !s->cur) {                  // a recalled slab left a sub-block tail: it needs a slab to travel in
+        rc = take_slab(e, s, g);
+        if (rc != DM_OK) return rc;
+        if (s->st == St::Finishing || s->st == St::Done) return DM_OK;      // someone else finished it while we waited
+    }
+    rc = submit_slab(e, sp);
     if (rc != DM_OK) return rc;
     while (!s->parts.empty()) {
         rc = submit_part(e, sp, s->parts.size() - 1);
@@ -1624,8 +1655,8 @@ int dm_stream_flush(dm_engine *e, uint64_t id)
     if (!e) return fail(DM_EINVAL, "null argument");
     auto sp = find_stream(e, id);
     if (!sp) return fail(DM_EINVAL, "unknown stream id");
-    std::lock_guard<std::mutex> g(sp->mu);
-    return begin_finish(e, sp);
+    std::unique_lock<std::mutex> g(sp->mu);
+    return begin_finish(e, sp, g);
 }
 
 int dm_stream_finish(dm_engine *e, uint64_t id, uint8_t digest_out[32], int *matched)
@@ -1637,7 +1668,7 @@ int dm_stream_finish(dm_engine *e, uint64_t id, uint8_t digest_out[32], int *mat
     std::shared_ptr<Blob> blob;
     {
         std::unique_lock<std::mutex> g(s->mu);
-        int rc = begin_finish(e, sp);
+        int rc = begin_finish(e, sp, g);
         if (rc != DM_OK) return rc;
         s->cv.wait(g, [&] { return s->st == St::Done; });
         if (digest_out) memcpy(digest_out, s->digest.b, 32);
@@ -1665,6 +1696,7 @@ int dm_stream_abort(dm_engine *e, uint64_t id)
         std::lock_guard<std::mutex> g(s->mu);
         if (s->st == St::Done || s->st == St::Aborted) return fail(DM_ESTATE, "stream already closed");
         if (s->cur) { slab_put(e, s->cur); s->cur = nullptr; s->cur_fill = 0; }
+        s->carry_fill = 0;
         for (Stream::Part &pt : s->parts) slab_put(e, pt.slab);
         s->parts.clear();
         if (!s->staged.empty()) {            // their DMAs may be in flight: drain before the ring reuses them

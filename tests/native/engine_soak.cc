@@ -24,6 +24,7 @@ extern "C" void dmo_sha256(const void *data, size_t len, uint8_t out[32]);
                                    failures.fetch_add(1); return; } } while (0)
 
 static std::atomic<int> failures{0};
+static std::atomic<int> where[64];             // op each worker is in (watchdog report)
 static std::atomic<long> ops{0}, enomem{0}, followed{0};
 
 struct Body { std::vector<uint8_t> bytes; uint8_t digest[32]; };
@@ -67,6 +68,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
         uint64_t id = 0;
         const int op = (int)(rng() % 15);
         ops++;
+        where[tid & 63] = op * 1000 + (int)(n >> 10);
         if (op <= 1) {                                               // sequential, random piece size
             rc = dm_stream_open(e, b.digest, (rng() & 1) ? n : 0, &id);
             if (tolerate(rc)) continue;
@@ -349,8 +351,9 @@ static void driver_phase(bool verify_only)
     dm_config cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.struct_size = sizeof cfg;
+    const char *drv_ring = getenv("RIG_DRV_RING");              // e.g. 262144: 4 slabs for 8 interleaved bodies per thread
     cfg.hbm_cas_bytes = 64u << 20;
-    cfg.ring_bytes = 2u << 20;
+    cfg.ring_bytes = drv_ring && *drv_ring ? strtoull(drv_ring, nullptr, 0) : 2u << 20;
     cfg.slab_bytes = 64u << 10;
     cfg.max_streams = 256;
     cfg.flags = verify_only ? DM_F_NO_HBM_CAS : 0;
@@ -422,9 +425,10 @@ int main(int argc, char **argv)
     memset(&cfg, 0, sizeof cfg);
     cfg.struct_size = sizeof cfg;
     cfg.device = 0;
-    cfg.hbm_cas_bytes = 6u << 20;              // tiny arena: eviction and ENOMEM are part of the test
-    cfg.ring_bytes = 1u << 20;                 // 16 slabs of 64 KiB for up to `threads` writers: back-pressure
-    cfg.slab_bytes = 64u << 10;
+    auto env_u64 = [](const char *name, uint64_t dflt) { const char *v = getenv(name); return v && *v ? strtoull(v, nullptr, 0) : dflt; };
+    cfg.hbm_cas_bytes = env_u64("RIG_ARENA", 6u << 20);      // tiny arena: eviction and ENOMEM are part of the test
+    cfg.ring_bytes = env_u64("RIG_RING", 1u << 20);          // 16 slabs of 64 KiB for up to `threads` writers: back-pressure
+    cfg.slab_bytes = (uint32_t)env_u64("RIG_SLAB", 64u << 10);
     cfg.max_streams = 256;
     cfg.cas_dir = cas_dir;
     cfg.flags = verify_only ? DM_F_NO_HBM_CAS : 0;
@@ -432,7 +436,31 @@ int main(int argc, char **argv)
     if (dm_engine_create(&cfg, &e) != DM_OK) { fprintf(stderr, "create failed: %s\n", dm_last_error()); return 1; }
     std::vector<std::thread> th;
     for (int t = 0; t < threads; ++t) th.emplace_back(worker, e, t, seconds, verify_only);
+    std::atomic<bool> done{false};
+    std::thread dog([&] {                        // a stuck engine must fail the test with a report, not hang it
+        long last = -1;
+        int still = 0;
+        while (!done.load()) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(500));
+            const long now = ops.load();
+            still = now == last ? still + 1 : 0;
+            last = now;
+            if (still == 40) {
+                dm_stats w;
+                dm_engine_stats(e, &w);
+                fprintf(stderr, "STUCK for 20 s: open_streams=%llu open_readers=%llu slabs free/total=%llu/%llu hbm_used=%llu ring_waits=%llu launches=%llu\n",
+                        (unsigned long long)w.open_streams, (unsigned long long)w.open_readers, (unsigned long long)w.ring_slabs_free,
+                        (unsigned long long)w.ring_slabs_total, (unsigned long long)w.hbm_cas_used, (unsigned long long)w.ring_waits,
+                        (unsigned long long)w.kernel_launches);
+                for (int t = 0; t < threads && t < 64; ++t) fprintf(stderr, "  worker %d: op %d, body %d KiB\n", t, where[t].load() / 1000, where[t].load() % 1000);
+                fprintf(stderr, "ENGINE SOAK FAILED (stuck)\n");
+                _Exit(3);
+            }
+        }
+    });
     for (auto &t : th) t.join();
+    done = true;
+    dog.join();
     dm_stats st;
     for (int i = 0; i < 500; ++i) {
         dm_engine_stats(e, &st);

@@ -59,11 +59,15 @@ def test_engine_host_logic_soak_under_tsan_and_asan(tmp_path):
             if "sanitize" in build.stderr.lower() or "asan" in build.stderr.lower() or "tsan" in build.stderr.lower():
                 continue                                          # this toolchain lacks that sanitizer runtime
             raise AssertionError(build.stderr[-3000:])
-        env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66", ASAN_OPTIONS="detect_leaks=0")
-        # the last run delays every queued operation by a random 0..300 us: real hardware's enqueue-to-execute gap
-        for mode, jitter in ((["3", "6"], "0"), (["3", "6", str(tmp_path / f"cas_{name}")], "0"), (["3", "6", "", "1"], "0"),
-                             (["3", "6"], "300")):
-            env["FAKE_CUDA_JITTER_US"] = jitter
+        base_env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66", ASAN_OPTIONS="detect_leaks=0")
+        # the fourth run delays every queued operation by a random 0..300 us: real hardware's enqueue-to-execute gap
+        # then: a 4-slab ring under 8 writers (parallel range parts and idle bodies pin partly filled slabs: the pump
+        # must recall them, verify-only streams keeping their sub-block tail) - a stuck engine fails via the watchdog
+        starved = {"RIG_SLAB": "4096", "RIG_RING": "16384", "RIG_DRV_RING": "262144"}
+        for mode, jitter, geo in ((["3", "6"], "0", {}), (["3", "6", str(tmp_path / f"cas_{name}")], "0", {}),
+                                  (["3", "6", "", "1"], "0", {}), (["3", "6"], "300", {}),
+                                  (["3", "8"], "0", starved), (["3", "8", "", "1"], "0", starved)):
+            env = dict(base_env, FAKE_CUDA_JITTER_US=jitter, **geo)
             out = subprocess.run([str(exe), *mode], capture_output=True, text=True, timeout=300, env=env)
             text = out.stdout + out.stderr
             assert out.returncode == 0 and "ENGINE SOAK OK" in out.stdout, text[-4000:]
