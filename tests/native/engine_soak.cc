@@ -26,6 +26,7 @@ extern "C" void dmo_sha256(const void *data, size_t len, uint8_t out[32]);
 static std::atomic<int> failures{0};
 static std::atomic<int> where[64];             // op each worker is in (watchdog report)
 static std::atomic<long> ops{0}, enomem{0}, followed{0};
+static uint64_t g_arena = 0;                   // a body larger than the arena is verified only: no out-of-order ranges
 
 struct Body { std::vector<uint8_t> bytes; uint8_t digest[32]; };
 static std::vector<Body> bodies;
@@ -63,6 +64,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
         const Body &b = bodies[rng() % bodies.size()];
         const size_t n = b.bytes.size();
         const uint8_t *p = b.bytes.data();
+        const bool vo = verify_only || n > g_arena;                  // larger than the arena: verified, never stored
         uint8_t got[32];
         int matched = -1, rc;
         uint64_t id = 0;
@@ -86,7 +88,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
             if (rc == 1) continue;
             CHECK(rc == DM_OK);
             CHECK(matched == 1 && memcmp(got, b.digest, 32) == 0);
-        } else if (op == 2 && n > 1000 && !verify_only) {            // three range parts, pieces interleaved
+        } else if (op == 2 && n > 1000 && !vo) {            // three range parts, pieces interleaved
             rc = dm_stream_open(e, b.digest, n, &id);
             if (tolerate(rc)) continue;
             CHECK(rc == DM_OK);
@@ -163,7 +165,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
             size_t mlen = 0;
             CHECK(dm_cache_meta(e, rid, meta, sizeof meta, &mlen) == DM_OK && mlen > 10);
             CHECK(dm_cache_close(e, rid) == DM_OK);
-        } else if (op == 8 && !verify_only) {                        // coalesce onto an in-flight body
+        } else if (op == 8 && !vo) {                        // coalesce onto an in-flight body
             uint64_t rid = 0, hint = 0;
             if (dm_cache_follow(e, b.digest, &rid, &hint) != DM_OK) continue;
             size_t off = 0, nread = 0;
@@ -190,12 +192,12 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
             dm_checkpoint ck;
             rc = dm_stream_checkpoint(e, id, &ck);
             if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); continue; }
-            CHECK(ck.bytes <= cut && ck.bytes % 64 == 0 && (verify_only || ck.bytes == cut / 64 * 64));
+            CHECK(ck.bytes <= cut && ck.bytes % 64 == 0 && (vo || ck.bytes == cut / 64 * 64));
             CHECK(dm_stream_abort(e, id) == DM_OK);
             rc = dm_stream_resume(e, &ck, b.digest, n, &id);
             if (tolerate(rc)) continue;
             CHECK(rc == DM_OK);
-            if ((rng() & 1) && !verify_only && ck.bytes) {
+            if ((rng() & 1) && !vo && ck.bytes) {
                 rc = dm_stream_write_at(e, id, 0, p, ck.bytes);
                 if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); continue; }
             }
@@ -205,7 +207,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
             if (rc == 1) continue;
             CHECK(rc == DM_OK);
             CHECK(matched == 1 && memcmp(got, b.digest, 32) == 0);
-        } else if (op == 12 && !verify_only) {                       // a ragged batch already "in HBM": one launch
+        } else if (op == 12 && !vo) {                       // a ragged batch already "in HBM": one launch
             const uint32_t nb = 1 + (uint32_t)(rng() % 24);
             std::vector<uint64_t> off(nb), len(nb);
             uint64_t pos = 0;
@@ -273,7 +275,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
             if (rc == 1) continue;
             CHECK(rc == DM_OK && matched == 1);
             uint64_t rid = 0, size = 0;
-            if (!verify_only && dm_cache_open(e, b.digest, &rid, &size) == DM_OK) {
+            if (!vo && dm_cache_open(e, b.digest, &rid, &size) == DM_OK) {
                 char meta[1024];
                 size_t mlen = 0;
                 CHECK(dm_cache_meta(e, rid, meta, sizeof meta, &mlen) == DM_OK && mlen < sizeof meta);
@@ -323,7 +325,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
             CHECK(dm_stream_write(e, id, scratch.data(), 1) < 0);
             CHECK(dm_stream_abort(e, id) < 0);
             uint64_t rid = 0, size = 0;
-            if (!verify_only && dm_cache_open(e, got, &rid, &size) == DM_OK) {
+            if (!vo && dm_cache_open(e, got, &rid, &size) == DM_OK) {
                 CHECK(size == std::min<size_t>(n, 5000));
                 CHECK(dm_cache_read(e, rid, size + 1, scratch.data(), 1, &nread) == DM_ERANGE);
                 CHECK(dm_cache_read(e, rid, size, scratch.data(), 1, &nread) == DM_OK && nread == 0);      // EOF
@@ -426,7 +428,7 @@ int main(int argc, char **argv)
     cfg.struct_size = sizeof cfg;
     cfg.device = 0;
     auto env_u64 = [](const char *name, uint64_t dflt) { const char *v = getenv(name); return v && *v ? strtoull(v, nullptr, 0) : dflt; };
-    cfg.hbm_cas_bytes = env_u64("RIG_ARENA", 6u << 20);      // tiny arena: eviction and ENOMEM are part of the test
+    cfg.hbm_cas_bytes = g_arena = env_u64("RIG_ARENA", 6u << 20);   // tiny arena: eviction and ENOMEM are part of the test
     cfg.ring_bytes = env_u64("RIG_RING", 1u << 20);          // 16 slabs of 64 KiB for up to `threads` writers: back-pressure
     cfg.slab_bytes = (uint32_t)env_u64("RIG_SLAB", 64u << 10);
     cfg.max_streams = 256;
