@@ -416,6 +416,50 @@ static void driver_phase(bool verify_only)
     dm_engine_destroy(e);
 }
 
+// Shutdown with transfers in flight: the proxy is stopped while bodies are half way and hits are being served.
+// Destroy must not hang, crash or touch freed memory (ASan), whatever state the streams and readers are in.
+static void destroy_with_open_handles(const char *cas_dir)
+{
+    dm_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = sizeof cfg;
+    cfg.hbm_cas_bytes = 16u << 20;
+    cfg.ring_bytes = 512u << 10;
+    cfg.slab_bytes = 64u << 10;
+    cfg.max_streams = 64;
+    cfg.cas_dir = cas_dir;
+    dm_engine *e = nullptr;
+    CHECK(dm_engine_create(&cfg, &e) == DM_OK);
+    const Body &big = bodies.back();
+    uint64_t id = 0, rid = 0, size = 0;
+    uint8_t got[32];
+    int matched = 0;
+    CHECK(dm_stream_open(e, big.digest, big.bytes.size(), &id) == DM_OK);                 // a finished, cached blob with an open reader
+    CHECK(dm_stream_write(e, id, big.bytes.data(), big.bytes.size()) == DM_OK);
+    CHECK(dm_stream_finish(e, id, got, &matched) == DM_OK && matched == 1);
+    CHECK(dm_cache_open(e, big.digest, &rid, &size) == DM_OK);
+    std::vector<uint8_t> buf(100000);
+    size_t nread = 0;
+    CHECK(dm_cache_read(e, rid, 0, buf.data(), buf.size(), &nread) == DM_OK);            // read-ahead windows in flight
+    const Body &b1 = bodies[bodies.size() - 2], &b2 = bodies[bodies.size() - 3];
+    uint64_t s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+    CHECK(dm_stream_open(e, b1.digest, b1.bytes.size(), &s1) == DM_OK);                  // half-written body
+    CHECK(dm_stream_write(e, s1, b1.bytes.data(), b1.bytes.size() / 2 + 13) == DM_OK);
+    CHECK(dm_stream_open(e, b2.digest, b2.bytes.size(), &s2) == DM_OK);                  // range parts with holes
+    CHECK(dm_stream_write_at(e, s2, 100000, b2.bytes.data() + 100000, 5000) == DM_OK);
+    CHECK(dm_stream_write_at(e, s2, 200000, b2.bytes.data() + 200000, 70001) == DM_OK);
+    CHECK(dm_stream_open(e, nullptr, 0, &s3) == DM_OK);                                   // a lent-out zero-copy window
+    void *win = nullptr;
+    size_t cap = 0;
+    CHECK(dm_stream_acquire(e, s3, &win, &cap) == DM_OK);
+    CHECK(dm_stream_open(e, b1.digest, 0, &s4) == DM_OK);                                 // flushed, verdict never collected
+    CHECK(dm_stream_write(e, s4, b1.bytes.data(), b1.bytes.size()) == DM_OK);
+    CHECK(dm_stream_flush(e, s4) == DM_OK);
+    uint64_t fr = 0, hint = 0;
+    (void)dm_cache_follow(e, b1.digest, &fr, &hint);                                      // a follower attached to s1 (may be refused)
+    dm_engine_destroy(e);
+}
+
 int main(int argc, char **argv)
 {
     const double seconds = argc > 1 ? atof(argv[1]) : 5.0;
@@ -476,6 +520,7 @@ int main(int argc, char **argv)
            (unsigned long long)st.blobs_mismatched, (unsigned long long)st.ring_waits, (int)clean, failures.load());
     dm_engine_destroy(e);
     if (!failures.load()) driver_phase(verify_only);
+    if (!failures.load() && !verify_only) destroy_with_open_handles(cas_dir);
     if (failures.load() || !clean) { printf("ENGINE SOAK FAILED\n"); return 1; }
     printf("ENGINE SOAK OK\n");
     return 0;
