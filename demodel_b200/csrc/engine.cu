@@ -1459,6 +1459,7 @@ int dm_stream_write(dm_engine *e, uint64_t id, const void *buf, size_t len)
 int dm_stream_write_at(dm_engine *e, uint64_t id, uint64_t offset, const void *buf, size_t len)
 {
     if (!e || (!buf && len)) return fail(DM_EINVAL, "null argument");
+    if (offset + len < offset) return fail(DM_ERANGE, "offset + len overflows");
     auto sp = find_stream(e, id);
     if (!sp) return fail(DM_EINVAL, "unknown stream id");
     Stream *s = sp.get();

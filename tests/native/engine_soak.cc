@@ -313,6 +313,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
                 CHECK(dm_stream_commit(e, id, cap + 1) == DM_EINVAL);
                 CHECK(dm_stream_commit(e, id, 0) == DM_OK);
                 CHECK(dm_stream_commit(e, id, 0) == DM_ESTATE);
+                CHECK(dm_stream_write_at(e, id, ~0ull - 10, scratch.data(), 100) == DM_ERANGE);
             } else {
                 CHECK(tolerate(rc));
             }
