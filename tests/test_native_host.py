@@ -2,6 +2,7 @@
 allocator and the interval set behind range parts.  Runs on the CPU-only box."""
 import os
 import subprocess
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -90,3 +91,20 @@ def test_every_round_form_is_sha256_on_the_host(tmp_path):
                     os.path.join(ROOT, "tests", "native", "test_round_forms.cc"), str(obj), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "ROUND FORMS OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_python_mirror_and_gpu_test_logic_over_the_fake_runtime(tmp_path):
+    """The host-buffer tests of test_gpu_parity.py / test_manifest.py, run here against the engine built over the
+    fake CUDA runtime (its 'kernels' are the CPU oracle): exercises the ctypes mirror and the tests' own logic on
+    the CPU box, in a subprocess that patches the loader path for itself only.  Not a parity claim."""
+    lib = tmp_path / "libdemodel_b200_fake.so"
+    cs = os.path.join(ROOT, "demodel_b200", "csrc")
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread",
+                            "-I", os.path.join(ROOT, "tests", "native", "fake_cuda"), "-o", str(lib), "-x", "c++",
+                            os.path.join(cs, "engine.cu"), os.path.join(cs, "proxy_driver.cc"), os.path.join(cs, "manifest.cc"),
+                            os.path.join(ROOT, "tests", "native", "fake_cuda.cc")], capture_output=True, text=True, timeout=600)
+    assert build.returncode == 0, build.stderr[-3000:]
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "native", "run_mirror_tests.py"), str(lib)],
+                         capture_output=True, text=True, timeout=900)
+    tail = (out.stdout + out.stderr)[-4000:]
+    assert out.returncode == 0 and " 0 failed, leak=0" in out.stdout, tail
