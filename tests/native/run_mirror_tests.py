@@ -84,6 +84,8 @@ def main():
     cases = [(name, fn) for mod in (T, TM) for name, fn in sorted(vars(mod).items())
              if name.startswith("test_") and callable(fn) and is_gpu(mod, fn)]
     for name, fn in cases:
+        if name in ("test_baseline_sized_properties", "test_ollama_pull_at_the_fixture_sizes"):
+            continue                                      # GiB-sized bodies through the scalar oracle: too slow for the CPU suite
         params = list(inspect.signature(fn).parameters)
         variants = [{}]
         for mark in getattr(fn, "pytestmark", []):
