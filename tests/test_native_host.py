@@ -93,7 +93,7 @@ def test_every_round_form_is_sha256_on_the_host(tmp_path):
     assert out.returncode == 0 and "ROUND FORMS OK" in out.stdout, out.stdout + out.stderr
 
 
-def test_python_mirror_and_gpu_test_logic_over_the_fake_runtime(tmp_path):
+def test_python_mirror_gpu_test_logic_and_bench_flow_over_the_fake_runtime(tmp_path):
     """The host-buffer tests of test_gpu_parity.py / test_manifest.py, run here against the engine built over the
     fake CUDA runtime (its 'kernels' are the CPU oracle): exercises the ctypes mirror and the tests' own logic on
     the CPU box, in a subprocess that patches the loader path for itself only.  Not a parity claim."""
@@ -108,3 +108,19 @@ def test_python_mirror_and_gpu_test_logic_over_the_fake_runtime(tmp_path):
                          capture_output=True, text=True, timeout=900)
     tail = (out.stdout + out.stderr)[-4000:]
     assert out.returncode == 0 and " 0 failed, leak=0" in out.stdout, tail
+    # bench.py's whole control flow over the same build (numbers meaningless): it must reach its JSON line with
+    # every key of the contract, in both arms
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "native", "run_bench_over_fake.py"), str(lib),
+                          "--workload", "tiny", "--steps", "2", "--warmup", "1", "--no-probes"],
+                         capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    assert out.returncode == 0, (out.stdout + out.stderr)[-4000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "int_issue"} <= set(line["roofline"])
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+    assert line["warmup"] >= 3 and line["gpu_launches"] > 0 and line["config"]["workload"] == "tiny"
+    assert line["e2e"]["h2d_bytes_per_step"] == line["config"]["bytes_per_gpu_per_step"]
