@@ -298,7 +298,11 @@ struct dm_engine {
     cudaEvent_t ing_ev0{}, ing_ev1{};
 
     // stats
-    std::atomic<uint64_t> st_ingested{0}, st_hashed{0}, st_served{0}, st_committed{0}, st_mismatch{0};
+    // the two counters bumped from caller threads sit on cache lines of their own (many writers / readers at once)
+    alignas(64) std::atomic<uint64_t> st_ingested{0};
+    alignas(64) std::atomic<uint64_t> st_served{0};
+    alignas(64) std::atomic<uint64_t> st_hashed{0};
+    std::atomic<uint64_t> st_committed{0}, st_mismatch{0};
     std::atomic<uint64_t> st_group{0};
     std::atomic<uint64_t> st_launches{0}, st_wide{0}, st_deep{0}, st_h2d{0}, st_d2h{0}, st_ring_waits{0};
     std::mutex stat_mu;
@@ -506,6 +510,7 @@ int submit_slab(dm_engine *e, const std::shared_ptr<Stream> &sp)
     const uint32_t n = s->cur_fill;
     s->cur = nullptr; s->cur_fill = 0;
     if (n == 0) { slab_put(e, slab); return DM_OK; }
+    e->st_ingested.fetch_add(n, std::memory_order_relaxed);       // per slab, not per write: one shared line, many writer threads
     if (s->verify_only) {
         cudaSetDevice(e->device);
         cudaError_t err = cudaMemcpyAsync(slab->dev, slab->host, n, cudaMemcpyHostToDevice, e->copy_stream[s->id % kCopyStreams]);
@@ -532,6 +537,7 @@ int submit_part(dm_engine *e, const std::shared_ptr<Stream> &sp, size_t idx)
     Stream::Part pt = s->parts[idx];
     s->parts.erase(s->parts.begin() + (long)idx);
     if (pt.fill == 0) { slab_put(e, pt.slab); return DM_OK; }
+    e->st_ingested.fetch_add(pt.fill, std::memory_order_relaxed);
     int rc = dma_range(e, sp, pt.slab, pt.base, pt.fill);
     if (rc != DM_OK) return rc;
     if (pt.base + pt.fill <= s->resume_base) add_interval(s->prefix_cover, pt.base, pt.base + pt.fill);
@@ -1447,7 +1453,6 @@ int dm_stream_write(dm_engine *e, uint64_t id, const void *buf, size_t len)
             return fail(DM_EINVAL, "write overlaps a range already received");
         memcpy(s->cur->host + s->cur_fill, p, n);
         s->cur_fill += (uint32_t)n; s->received += n; p += n; len -= n;
-        e->st_ingested += n;
         if (s->cur_fill == slab_bytes) {
             int rc = submit_slab(e, sp);
             if (rc != DM_OK) return rc;
@@ -1489,7 +1494,6 @@ int dm_stream_write_at(dm_engine *e, uint64_t id, uint64_t offset, const void *b
                 if (range_taken(s, offset, n, nullptr)) return fail(DM_EINVAL, "write overlaps a range already received");
                 memcpy(s->cur->host + s->cur_fill, p, n);
                 s->cur_fill += (uint32_t)n; s->received += n; p += n; len -= n; offset += n;
-                e->st_ingested += n;
                 if (s->cur_fill == slab_bytes) { int rc = submit_slab(e, sp); if (rc != DM_OK) return rc; }
                 continue;
             }
@@ -1508,7 +1512,6 @@ int dm_stream_write_at(dm_engine *e, uint64_t id, uint64_t offset, const void *b
         if (range_taken(s, offset, n, &pt)) return fail(DM_EINVAL, "write overlaps a range already received");
         memcpy(pt.slab->host + pt.fill, p, n);
         pt.fill += (uint32_t)n; s->received += n; p += n; len -= n; offset += n;
-        e->st_ingested += n;
         if (pt.fill == slab_bytes) { int rc = submit_part(e, sp, idx); if (rc != DM_OK) return rc; }
     }
     return DM_OK;
@@ -1622,7 +1625,6 @@ int dm_stream_commit(dm_engine *e, uint64_t id, size_t len)
     if (len > e->cfg.slab_bytes - s->cur_fill) return fail(DM_EINVAL, "commit larger than the window");
     s->window_out = false;
     s->cur_fill += (uint32_t)len; s->received += len;
-    e->st_ingested += len;
     if (s->cur_fill == e->cfg.slab_bytes) return submit_slab(e, sp);
     return DM_OK;
 }
@@ -1966,7 +1968,7 @@ int dm_cache_read(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t
         }
         bounce_put(e, bn);
     }
-    e->st_served += done;
+    e->st_served.fetch_add(done, std::memory_order_relaxed);
     if (nread) *nread = done;
     return rc;
 }

@@ -72,7 +72,7 @@ typedef struct dm_config {
 } dm_config;
 
 typedef struct dm_stats {
-    uint64_t bytes_ingested;      /* through dm_stream_write/commit */
+    uint64_t bytes_ingested;      /* through dm_stream_write/write_at/commit, counted per slab as it goes to the device */
     uint64_t bytes_hashed;        /* by the SHA-256 kernels */
     uint64_t bytes_served;        /* through dm_cache_read */
     uint64_t blobs_committed;
