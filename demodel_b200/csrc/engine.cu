@@ -181,6 +181,7 @@ struct Stream {
     St st = St::Open;
     Digest digest{};
     int matched = 0;
+    bool cuda_failed = false;  // a copy or launch for this stream failed: whatever digest comes back is not trusted
     int result = DM_OK;
     std::shared_ptr<Blob> blob;   // set at commit
 };
@@ -212,6 +213,7 @@ struct Cycle {
     std::vector<std::shared_ptr<Stream>> streams;   // one entry per job
     std::vector<Slab *> job_slabs;                  // verify-only jobs: the ring slab to release at reap
     std::vector<uint8_t> is_final;
+    cudaError_t err = cudaSuccess;                  // first failure while building or running this launch
 };
 
 struct SlabBatch {
@@ -485,7 +487,7 @@ int dma_range(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *slab, uint6
         if (err == cudaSuccess) err = cudaMemcpyAsync(dev, src, len, cudaMemcpyHostToDevice, cs);
         src += len;
     });
-    if (err != cudaSuccess) { slab_put(e, slab); return fail_cuda(err, "cudaMemcpyAsync(H2D slab)"); }
+    if (err != cudaSuccess) { s->cuda_failed = true; slab_put(e, slab); return fail_cuda(err, "cudaMemcpyAsync(H2D slab)"); }
     e->st_h2d += n;
     return DM_OK;
 }
@@ -736,6 +738,7 @@ void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint
     if (s->st == St::Aborted) return;
     words_to_digest(words, s->digest.b);
     s->matched = (!s->has_expect || s->digest == s->expect) ? 1 : 0;
+    if (s->cuda_failed) { s->matched = 0; memset(s->digest.b, 0, 32); }     // never publish under a digest the device may not have produced
     s->completing = true;                       // no new follower copy-out starts past this point
     wait_follow_reads(s, g);
     std::vector<Extent> ext;
@@ -777,6 +780,7 @@ void reap_cycle(dm_engine *e, Cycle &c)
         bool free_now = false, wake = false;
         {
             std::lock_guard<std::mutex> g(sp->mu);
+            if (c.err != cudaSuccess) sp->cuda_failed = true;
             sp->jobs_inflight--;
             free_now = sp->st == St::Aborted && sp->jobs_inflight == 0;
             wake = sp->ckpt_waiter;
@@ -794,7 +798,7 @@ void reap_cycle(dm_engine *e, Cycle &c)
         }
     }
     c.streams.clear(); c.is_final.clear();
-    c.njobs = 0; c.bytes = 0; c.busy = false;
+    c.njobs = 0; c.bytes = 0; c.busy = false; c.err = cudaSuccess;
 }
 
 // Build one job per eligible ready stream and launch ONE multi-buffer kernel
@@ -876,13 +880,17 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
         for (uint32_t i = 0; i < c.njobs; ++i) { c.h_jobs[i] = tmp[order[i]]; st2[i] = c.streams[order[i]]; fin2[i] = c.is_final[order[i]]; sl2[i] = c.job_slabs[order[i]]; }
         c.streams.swap(st2); c.is_final.swap(fin2); c.job_slabs.swap(sl2);
     }
-    cudaMemcpyAsync(c.d_jobs, c.h_jobs, sizeof(dm::HashJob) * c.njobs, cudaMemcpyHostToDevice, c.stream);
-    cudaEventRecord(c.k_start, c.stream);
-    if (spw == 1) { dm::launch_sha256_deep(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_deep); e->st_deep++; }
-    else if (spw == 32) { dm::launch_sha256_wide(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_wide); e->st_wide++; }
-    else { dm::launch_sha256_group(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, spw, e->variant_deep); e->st_group++; }
+    // A failure anywhere here (or reported later by the end event) marks every stream of the launch:
+    // their verdict becomes "not matched" and nothing is published (reap_cycle / complete_stream).
+    auto note = [&](cudaError_t r) { if (r != cudaSuccess && c.err == cudaSuccess) c.err = r; };
+    note(cudaMemcpyAsync(c.d_jobs, c.h_jobs, sizeof(dm::HashJob) * c.njobs, cudaMemcpyHostToDevice, c.stream));
+    note(cudaEventRecord(c.k_start, c.stream));
+    if (c.err != cudaSuccess) { /* the job table may not be on the device: launching would run stale jobs */ }
+    else if (spw == 1) { note(dm::launch_sha256_deep(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_deep)); e->st_deep++; }
+    else if (spw == 32) { note(dm::launch_sha256_wide(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_wide)); e->st_wide++; }
+    else { note(dm::launch_sha256_group(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, spw, e->variant_deep)); e->st_group++; }
     e->st_launches++;
-    cudaEventRecord(c.k_end, c.stream);
+    note(cudaEventRecord(c.k_end, c.stream));
     c.busy = true;
     return true;
 }
@@ -951,7 +959,12 @@ void pump_main(dm_engine *e)
         // 2. finished hash launches (any order)
         bool reaped = false;
         for (Cycle &c : e->cycles)
-            if (c.busy && cudaEventQuery(c.k_end) == cudaSuccess) { reap_cycle(e, c); --n_inflight; reaped = true; }
+            if (c.busy) {
+                const cudaError_t q = cudaEventQuery(c.k_end);
+                if (q == cudaErrorNotReady) continue;
+                if (q != cudaSuccess && c.err == cudaSuccess) c.err = q;       // a faulted launch must end, not hang its streams
+                reap_cycle(e, c); --n_inflight; reaped = true;
+            }
         // 3. inbox.  Sleep unless the previous pass launched something (more may be launchable).
         bool stopping;
         {
@@ -1525,6 +1538,7 @@ int dm_stream_checkpoint(dm_engine *e, uint64_t id, dm_checkpoint *out)
     Stream *s = sp.get();
     std::unique_lock<std::mutex> g(s->mu);
     if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open");
+    if (s->cuda_failed) return fail(DM_ECUDA, "a CUDA copy or launch failed earlier on this stream: its state is not trusted");
     if (!s->verify_only || (s->cur_fill & 63) == 0) {
         // push out what is staged so the checkpoint covers every whole block received in order
         // (a verify-only stream hashes slab by slab, so only a block-aligned partial slab may go early)
@@ -1536,6 +1550,7 @@ int dm_stream_checkpoint(dm_engine *e, uint64_t id, dm_checkpoint *out)
     s->cv.wait(g, [&] { return s->st != St::Open || (s->jobs_inflight == 0 && ((s->dma_issued - s->hash_issued) & ~63ull) == 0); });
     s->ckpt_waiter = false;
     if (s->st != St::Open) return fail(DM_ESTATE, "stream closed during checkpoint");
+    if (s->cuda_failed) return fail(DM_ECUDA, "a CUDA copy or launch failed on this stream: its state is not trusted");
     memset(out, 0, sizeof *out);
     out->abi = DM_ABI_VERSION;
     out->bytes = s->hash_issued;
@@ -1561,7 +1576,7 @@ int dm_stream_resume(dm_engine *e, const dm_checkpoint *ck, const uint8_t expect
     if (rc != DM_OK) return rc;
     auto sp = find_stream(e, *id);
     Stream *s = sp.get();
-    std::lock_guard<std::mutex> g(s->mu);
+    std::unique_lock<std::mutex> g(s->mu);
     s->resume_base = s->dma_issued = s->hash_issued = ck->bytes;
     if (ck->bytes && s->has_expect) {
         // not followable: the prefix may never be re-supplied, so there is nothing to serve from offset 0
@@ -1578,7 +1593,15 @@ int dm_stream_resume(dm_engine *e, const dm_checkpoint *ck, const uint8_t expect
         memcpy(e->ckpt_pinned, ck->h, 32);
         cudaError_t err = cudaMemcpyAsync(e->d_states + 8ull * s->slot, e->ckpt_pinned, 32, cudaMemcpyHostToDevice, e->ckpt_stream);
         if (err == cudaSuccess) err = cudaStreamSynchronize(e->ckpt_stream);
-        if (err != cudaSuccess) { s->st = St::Aborted; return fail_cuda(err, "cudaMemcpyAsync(checkpoint state)"); }
+        if (err != cudaSuccess) {
+            // nothing of this stream is in flight yet: give back its extent, state slot and id
+            s->st = St::Aborted;
+            g.unlock();
+            free_extents(e, s->extents);
+            drop_stream(e, sp, true);
+            *id = 0;
+            return fail_cuda(err, "cudaMemcpyAsync(checkpoint state)");
+        }
     }
     return DM_OK;
 }
@@ -1635,6 +1658,7 @@ static int begin_finish(dm_engine *e, const std::shared_ptr<Stream> &sp, std::un
     Stream *s = sp.get();
     if (s->st == St::Finishing || s->st == St::Done) return DM_OK;
     if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open");
+    if (s->cuda_failed) return fail(DM_ECUDA, "a CUDA copy or launch failed earlier on this stream (bytes may be missing): abort it");
     int rc = DM_OK;
     if (s->carry_fill && !s->cur) {                  // a recalled slab left a sub-block tail: it needs a slab to travel in
         rc = take_slab(e, s, g);
@@ -1669,6 +1693,7 @@ int dm_stream_finish(dm_engine *e, uint64_t id, uint8_t digest_out[32], int *mat
     if (!sp) return fail(DM_EINVAL, "unknown stream id");
     Stream *s = sp.get();
     std::shared_ptr<Blob> blob;
+    bool failed = false;
     {
         std::unique_lock<std::mutex> g(s->mu);
         int rc = begin_finish(e, sp, g);
@@ -1677,8 +1702,10 @@ int dm_stream_finish(dm_engine *e, uint64_t id, uint8_t digest_out[32], int *mat
         if (digest_out) memcpy(digest_out, s->digest.b, 32);
         if (matched) *matched = s->matched;
         blob = s->blob;
+        failed = s->cuda_failed;
     }
     drop_stream(e, sp, true);
+    if (failed) return fail(DM_ECUDA, "a CUDA copy or launch failed while this stream was being hashed; nothing was cached");
     if (blob && (e->cfg.flags & DM_F_DISK_SYNC) && !e->cas_dir.empty()) {
         std::unique_lock<std::mutex> g(e->spill_mu);
         e->spill_done_cv.wait(g, [&] { std::lock_guard<std::mutex> g2(e->mu); return blob->spill_done; });
@@ -2154,7 +2181,11 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
     if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev1, st);
     if (err == cudaSuccess) err = cudaMemcpyAsync(e->ing_digests_h, e->ing_digests, 32ull * n, cudaMemcpyDeviceToHost, st);
     if (err == cudaSuccess) err = cudaStreamSynchronize(st);
-    if (err != cudaSuccess) { cleanup(); return fail_cuda(err, "dm_ingest_device launch"); }
+    if (err != cudaSuccess) {
+        cudaStreamSynchronize(st);      // whatever was enqueued before the failure still uses the job table and the extents
+        cleanup();
+        return fail_cuda(err, "dm_ingest_device launch");
+    }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e->ing_ev0, e->ing_ev1);
     if (kernel_ms) *kernel_ms = ms;
@@ -2220,7 +2251,8 @@ int dm_synth_fill_device_many(dm_engine *e, uint64_t seed, uint64_t first_blob, 
     if (err == cudaSuccess)
         err = dm::launch_synth_fill_many(seed, first_blob, dev_base, d_tab, d_tab + n, n, offsets[0],
                                          offsets[n - 1] + lengths[n - 1] - offsets[0], e->util_stream);
-    if (err == cudaSuccess) err = cudaStreamSynchronize(e->util_stream);
+    const cudaError_t sync = cudaStreamSynchronize(e->util_stream);     // also on failure: the table may still be in use
+    if (err == cudaSuccess) err = sync;
     cudaFree(d_tab);
     if (err != cudaSuccess) return fail_cuda(err, "dm_synth_fill_device_many");
     return DM_OK;

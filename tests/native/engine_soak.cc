@@ -44,7 +44,14 @@ static void make_bodies()
         }
 }
 
-static bool tolerate(int rc) { if (rc == DM_ENOMEM) { enomem++; return true; } return false; }
+static bool g_inject = false;                   // FAKE_CUDA_FAIL_PPM set: copies and launches fail at random
+static std::atomic<long> cuda_failed{0};
+static bool tolerate(int rc)
+{
+    if (rc == DM_ENOMEM) { enomem++; return true; }
+    if (rc == DM_ECUDA && g_inject) { cuda_failed++; return true; }      // reported, never silently wrong
+    return false;
+}
 
 // finish (optionally flushing first); a full arena at the last slab is legal: abort and report "skipped"
 static int finish_or_skip(dm_engine *e, uint64_t id, bool flush_first, uint8_t got[32], int *matched)
@@ -52,6 +59,12 @@ static int finish_or_skip(dm_engine *e, uint64_t id, bool flush_first, uint8_t g
     int rc = flush_first ? dm_stream_flush(e, id) : DM_OK;
     if (rc == DM_OK) rc = dm_stream_finish(e, id, got, matched);
     if (rc == DM_ENOMEM) { enomem++; dm_stream_abort(e, id); return 1; }
+    if (rc == DM_ECUDA && g_inject) {            // a device fault during this stream: verdict withheld, nothing cached
+        cuda_failed++;
+        dm_stream_abort(e, id);                  // no-op if finish got far enough to release the id (ids are never reused)
+        if (matched && *matched == 1) return DM_EINVAL;                  // ... and it must not have claimed a match
+        return 1;
+    }
     return rc;
 }
 
@@ -218,7 +231,9 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
             }
             std::vector<uint8_t> dev(pos + 16);                      // the rig's device memory is host memory
             const uint64_t first = 9000 + rng() % 100000;
-            CHECK(dm_synth_fill_device_many(e, 0xDE40DE1, first, dev.data(), off.data(), len.data(), nb) == DM_OK);
+            rc = dm_synth_fill_device_many(e, 0xDE40DE1, first, dev.data(), off.data(), len.data(), nb);
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
             std::vector<uint8_t> want(32 * nb), digs(32 * nb), mat(nb, 7);
             for (uint32_t i = 0; i < nb; ++i) dmo_sha256(dev.data() + off[i], len[i], &want[32 * i]);
             {   // the device generator must equal the host generator
@@ -468,6 +483,7 @@ int main(int argc, char **argv)
     const char *cas_dir = argc > 3 && argv[3][0] ? argv[3] : nullptr;
     const bool verify_only = argc > 4 && atoi(argv[4]) != 0;
     make_bodies();
+    g_inject = getenv("FAKE_CUDA_FAIL_PPM") != nullptr;
     dm_config cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.struct_size = sizeof cfg;
@@ -516,12 +532,16 @@ int main(int argc, char **argv)
     }
     const bool clean = st.open_streams == 0 && st.open_readers == 0 && st.ring_slabs_free == st.ring_slabs_total &&
                        st.free_stream_slots == 256;
+    if (!clean) printf("NOT CLEAN: open_streams=%llu open_readers=%llu slabs free/total=%llu/%llu free_stream_slots=%llu\n",
+                       (unsigned long long)st.open_streams, (unsigned long long)st.open_readers, (unsigned long long)st.ring_slabs_free,
+                       (unsigned long long)st.ring_slabs_total, (unsigned long long)st.free_stream_slots);
+    if (g_inject) printf("injected device faults surfaced as DM_ECUDA: %ld\n", cuda_failed.load());
     printf("ops=%ld enomem=%ld followed=%ld launches=%llu committed=%llu mismatched=%llu ring_waits=%llu clean=%d failures=%d\n",
            ops.load(), enomem.load(), followed.load(), (unsigned long long)st.kernel_launches, (unsigned long long)st.blobs_committed,
            (unsigned long long)st.blobs_mismatched, (unsigned long long)st.ring_waits, (int)clean, failures.load());
     dm_engine_destroy(e);
-    if (!failures.load()) driver_phase(verify_only);
-    if (!failures.load() && !verify_only) destroy_with_open_handles(cas_dir);
+    if (!failures.load() && !g_inject) driver_phase(verify_only);
+    if (!failures.load() && !verify_only && !g_inject) destroy_with_open_handles(cas_dir);
     if (failures.load() || !clean) { printf("ENGINE SOAK FAILED\n"); return 1; }
     printf("ENGINE SOAK OK\n");
     return 0;

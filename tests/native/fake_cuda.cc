@@ -90,6 +90,18 @@ struct fakeEvent { std::shared_ptr<EvState> st = std::make_shared<EvState>(); };
 static std::mutex g_reg_mu;
 static std::vector<fakeStream *> g_streams;
 
+// FAKE_CUDA_FAIL_PPM=n: each host-to-device copy and each kernel launch fails with probability n per million
+// (returns an error, does nothing) - what a device fault looks like to the engine.
+static bool inject_failure()
+{
+    static const unsigned ppm = [] { const char *v = getenv("FAKE_CUDA_FAIL_PPM"); return v ? (unsigned)atoi(v) : 0u; }();
+    if (!ppm) return false;
+    static std::atomic<uint64_t> seq{0x9e3779b97f4a7c15ull};
+    uint64_t x = seq.fetch_add(0x9e3779b97f4a7c15ull);
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+    return x % 1000000u < ppm;
+}
+
 static void on_stream(cudaStream_t s, std::function<void()> f)
 {
     if (!s) { f(); return; }              // legacy stream: synchronous
@@ -143,7 +155,7 @@ cudaError_t cudaMalloc(void **p, size_t n)
     reg_add(g_device, *p, n);
     return cudaSuccess;
 }
-cudaError_t cudaFree(void *p) { if (p) reg_del(g_device, p); free(p); return cudaSuccess; }
+cudaError_t cudaFree(void *p) { cudaDeviceSynchronize(); if (p) reg_del(g_device, p); free(p); return cudaSuccess; }   // implicit sync, as the real one
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned)
 {
     *p = calloc(1, n ? n : 1);
@@ -151,7 +163,7 @@ cudaError_t cudaHostAlloc(void **p, size_t n, unsigned)
     reg_add(g_pinned, *p, n);
     return cudaSuccess;
 }
-cudaError_t cudaFreeHost(void *p) { if (p) reg_del(g_pinned, p); free(p); return cudaSuccess; }
+cudaError_t cudaFreeHost(void *p) { cudaDeviceSynchronize(); if (p) reg_del(g_pinned, p); free(p); return cudaSuccess; }
 cudaError_t cudaHostGetDevicePointer(void **dev, void *host, unsigned)
 {
     if (!reg_has(g_pinned, host, 1)) misuse("cudaHostGetDevicePointer on memory that is not pinned");
@@ -177,6 +189,7 @@ cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind kind)
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind kind, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
+    if (kind == cudaMemcpyHostToDevice && inject_failure()) return cudaErrorUnknown;
     if (kind == cudaMemcpyHostToDevice && !reg_has(g_pinned, s, n)) {
         auto snap = std::make_shared<std::vector<uint8_t>>((const uint8_t *)s, (const uint8_t *)s + n);
         on_stream(st, [d, snap] { memcpy(d, snap->data(), snap->size()); });
@@ -280,6 +293,7 @@ static void run_job(const HashJob &jb, uint32_t *states, uint32_t *digests)
 // same stream delivered
 static cudaError_t run_all(const HashJob *jobs, uint32_t n, uint32_t *states, uint32_t *digests, cudaStream_t st)
 {
+    if (inject_failure()) return cudaErrorUnknown;
     on_stream(st, [jobs, n, states, digests] { for (uint32_t i = 0; i < n; ++i) run_job(jobs[i], states, digests); });
     return cudaSuccess;
 }

@@ -67,7 +67,10 @@ def test_engine_host_logic_soak_under_tsan_and_asan(tmp_path):
         starved = {"RIG_SLAB": "4096", "RIG_RING": "16384", "RIG_DRV_RING": "262144"}
         for mode, jitter, geo in ((["3", "6"], "0", {}), (["3", "6", str(tmp_path / f"cas_{name}")], "0", {}),
                                   (["3", "6", "", "1"], "0", {}), (["3", "6"], "300", {}),
-                                  (["3", "8"], "0", starved), (["3", "8", "", "1"], "0", starved)):
+                                  (["3", "8"], "0", starved), (["3", "8", "", "1"], "0", starved),
+                                  # 2 % of all host-to-device copies and launches fail: every fault must surface as
+                                  # DM_ECUDA - never a wrong verdict, wrong bytes, a leak or a hang
+                                  (["3", "6"], "0", {"FAKE_CUDA_FAIL_PPM": "20000"})):
             env = dict(base_env, FAKE_CUDA_JITTER_US=jitter, **geo)
             out = subprocess.run([str(exe), *mode], capture_output=True, text=True, timeout=300, env=env)
             text = out.stdout + out.stderr
