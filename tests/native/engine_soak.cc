@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
+#include <fstream>
 #include <random>
 #include <string>
 #include <thread>
@@ -169,7 +171,8 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
             size_t off = 0, nread = 0;
             const size_t piece = (op == 6) ? 32768 : 1 + rng() % 300000;
             while (off < n) {
-                CHECK(dm_cache_read(e, rid, off, scratch.data(), std::min(piece, scratch.size()), &nread) == DM_OK);
+                rc = dm_cache_read(e, rid, off, scratch.data(), std::min(piece, scratch.size()), &nread);
+                if (rc != DM_OK) { CHECK(tolerate(rc)); break; }                      // injected D2H fault: reported, reader still closes
                 CHECK(nread > 0 && memcmp(scratch.data(), p + off, nread) == 0);
                 off += nread;
                 if (op == 7 && n) off = std::min<size_t>(n, off + rng() % 1000);     // skip around a little
@@ -185,7 +188,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
             bool ok = true;
             for (;;) {
                 rc = dm_cache_read(e, rid, off, scratch.data(), 100000, &nread);
-                if (rc != DM_OK) { CHECK(rc == DM_ESTATE || rc == DM_ENOENT); ok = false; break; }
+                if (rc != DM_OK) { CHECK(rc == DM_ESTATE || rc == DM_ENOENT || tolerate(rc)); ok = false; break; }
                 if (nread == 0) break;
                 CHECK(off + nread <= n && memcmp(scratch.data(), p + off, nread) == 0);
                 off += nread;
@@ -540,6 +543,24 @@ int main(int argc, char **argv)
            ops.load(), enomem.load(), followed.load(), (unsigned long long)st.kernel_launches, (unsigned long long)st.blobs_committed,
            (unsigned long long)st.blobs_mismatched, (unsigned long long)st.ring_waits, (int)clean, failures.load());
     dm_engine_destroy(e);
+    if (cas_dir && std::filesystem::exists(cas_dir)) {       // the disk tier may hold only files that hash to their own name
+        long files = 0, bad = 0;
+        for (auto &ent : std::filesystem::recursive_directory_iterator(cas_dir)) {
+            if (!ent.is_regular_file()) continue;
+            const std::string name = ent.path().filename().string();
+            if (name.size() != 64) continue;                 // sidecars (.meta) and abandoned .part files are not blobs
+            std::ifstream f(ent.path(), std::ios::binary);
+            std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+            uint8_t d[32];
+            dmo_sha256(bytes.data(), bytes.size(), d);
+            char hex[65];
+            for (int i = 0; i < 32; ++i) snprintf(hex + 2 * i, 3, "%02x", d[i]);
+            ++files;
+            if (name != hex) { ++bad; fprintf(stderr, "disk tier file %s does not hash to its name\n", ent.path().c_str()); }
+        }
+        printf("disk tier: %ld blob files, %ld wrong\n", files, bad);
+        if (bad) failures.fetch_add(1);
+    }
     if (!failures.load() && !g_inject) driver_phase(verify_only);
     if (!failures.load() && !verify_only && !g_inject) destroy_with_open_handles(cas_dir);
     if (failures.load() || !clean) { printf("ENGINE SOAK FAILED\n"); return 1; }

@@ -190,6 +190,7 @@ cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind kin
 {
     if (n == 0) return cudaSuccess;
     if (kind == cudaMemcpyHostToDevice && inject_failure()) return cudaErrorUnknown;
+    if (kind == cudaMemcpyDeviceToHost && getenv("FAKE_CUDA_FAIL_D2H") && inject_failure()) return cudaErrorUnknown;
     if (kind == cudaMemcpyHostToDevice && !reg_has(g_pinned, s, n)) {
         auto snap = std::make_shared<std::vector<uint8_t>>((const uint8_t *)s, (const uint8_t *)s + n);
         on_stream(st, [d, snap] { memcpy(d, snap->data(), snap->size()); });
