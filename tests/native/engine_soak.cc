@@ -479,8 +479,25 @@ static void destroy_with_open_handles(const char *cas_dir)
     dm_engine_destroy(e);
 }
 
+// `engine_soak create`: one dm_engine_create / destroy.  With FAKE_CUDA_FAIL_ALLOC_NTH=k the k-th allocation fails:
+// exit 2 = create failed cleanly, 0 = it succeeded (k is past the last allocation).  Run under ASan + LSan.
+static int create_only()
+{
+    dm_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = sizeof cfg;
+    cfg.hbm_cas_bytes = 8u << 20; cfg.ring_bytes = 1u << 20; cfg.slab_bytes = 64u << 10; cfg.max_streams = 64;
+    cfg.cas_dir = "/tmp/dm_rig_create_cas";
+    dm_engine *e = nullptr;
+    const int rc = dm_engine_create(&cfg, &e);
+    if (rc != DM_OK) { if (e) { fprintf(stderr, "create failed but returned a handle\n"); return 1; } return 2; }
+    dm_engine_destroy(e);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc > 1 && strcmp(argv[1], "create") == 0) return create_only();
     const double seconds = argc > 1 ? atof(argv[1]) : 5.0;
     const int threads = argc > 2 ? atoi(argv[2]) : 6;
     const char *cas_dir = argc > 3 && argv[3][0] ? argv[3] : nullptr;

@@ -148,8 +148,18 @@ static bool reg_has(std::map<uintptr_t, size_t> &m, const void *p, size_t n)
     abort();
 }
 
+// FAKE_CUDA_FAIL_ALLOC_NTH=k: the k-th device / pinned allocation (and stream / event creation) of the process fails,
+// to walk dm_engine_create's unwinding.
+static bool alloc_should_fail()
+{
+    static const long nth = [] { const char *v = getenv("FAKE_CUDA_FAIL_ALLOC_NTH"); return v ? atol(v) : 0L; }();
+    static std::atomic<long> count{0};
+    return nth > 0 && ++count == nth;
+}
+
 cudaError_t cudaMalloc(void **p, size_t n)
 {
+    if (alloc_should_fail()) { *p = nullptr; return cudaErrorMemoryAllocation; }
     *p = malloc(n ? n : 1);
     if (!*p) return cudaErrorMemoryAllocation;
     reg_add(g_device, *p, n);
@@ -158,6 +168,7 @@ cudaError_t cudaMalloc(void **p, size_t n)
 cudaError_t cudaFree(void *p) { cudaDeviceSynchronize(); if (p) reg_del(g_device, p); free(p); return cudaSuccess; }   // implicit sync, as the real one
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned)
 {
+    if (alloc_should_fail()) { *p = nullptr; return cudaErrorMemoryAllocation; }
     *p = calloc(1, n ? n : 1);
     if (!*p) return cudaErrorMemoryAllocation;
     reg_add(g_pinned, *p, n);
@@ -202,6 +213,7 @@ cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind kin
 }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned)
 {
+    if (alloc_should_fail()) { *s = nullptr; return cudaErrorMemoryAllocation; }
     *s = new fakeStream();
     std::lock_guard<std::mutex> g(g_reg_mu);
     g_streams.push_back(*s);
@@ -219,8 +231,8 @@ cudaError_t cudaStreamDestroy(cudaStream_t s)
     return cudaSuccess;
 }
 cudaError_t cudaStreamSynchronize(cudaStream_t s) { if (s) s->drain(); return cudaSuccess; }
-cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new fakeEvent(); return cudaSuccess; }
-cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new fakeEvent(); return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *e) { if (alloc_should_fail()) { *e = nullptr; return cudaErrorMemoryAllocation; } *e = new fakeEvent(); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { if (alloc_should_fail()) { *e = nullptr; return cudaErrorMemoryAllocation; } *e = new fakeEvent(); return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t ev, cudaStream_t s)
 {

@@ -77,6 +77,19 @@ def test_engine_host_logic_soak_under_tsan_and_asan(tmp_path):
             assert out.returncode == 0 and "ENGINE SOAK OK" in out.stdout, text[-4000:]
             assert "WARNING: ThreadSanitizer" not in text and "ERROR: AddressSanitizer" not in text and "runtime error" not in text, text[-4000:]
             ran += 1
+        if name == "asan":
+            # dm_engine_create's unwinding: fail the k-th device / pinned allocation, stream or event creation for a
+            # spread of k (there are ~290 of them) - create must fail cleanly: no leak (LSan), no touch of freed memory
+            ks = list(range(1, 13)) + list(range(13, 330, 11))
+            seen_success = False
+            for k in ks:
+                env = dict(base_env, ASAN_OPTIONS="detect_leaks=1", FAKE_CUDA_FAIL_ALLOC_NTH=str(k))
+                out = subprocess.run([str(exe), "create"], capture_output=True, text=True, timeout=120, env=env)
+                text = out.stdout + out.stderr
+                assert "Sanitizer" not in text and "runtime error" not in text, f"k={k}\n" + text[-3000:]
+                assert out.returncode in (0, 2), f"k={k} rc={out.returncode}\n" + text[-2000:]
+                seen_success = seen_success or out.returncode == 0
+            assert seen_success, "the walk never got past the last allocation: extend ks"
     if ran == 0:
         exe = tmp_path / "rig_plain"                              # no sanitizer runtime at all: still run the soak
         build = _build_rig(exe)
