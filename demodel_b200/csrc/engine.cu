@@ -66,6 +66,16 @@ int fail(int code, const char *what)
     g_last_error = what ? what : "";
     return code;
 }
+// cudaEventQuery's "not ready" also lands in the runtime's per-thread last-error slot, where the next
+// `cudaGetLastError()` (the launch wrappers end in one) would find it and report a launch failure that never
+// happened.  Every poll goes through here.
+cudaError_t poll_event(cudaEvent_t ev)
+{
+    const cudaError_t q = cudaEventQuery(ev);
+    if (q == cudaErrorNotReady) (void)cudaGetLastError();
+    return q;
+}
+
 int fail_cuda(cudaError_t err, const char *where)
 {
     g_last_error = std::string(where) + ": " + cudaGetErrorString(err);
@@ -882,7 +892,8 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
     }
     // A failure anywhere here (or reported later by the end event) marks every stream of the launch:
     // their verdict becomes "not matched" and nothing is published (reap_cycle / complete_stream).
-    auto note = [&](cudaError_t r) { if (r != cudaSuccess && c.err == cudaSuccess) c.err = r; };
+    (void)cudaGetLastError();           // nothing stale may be mistaken for this launch's result
+    auto note = [&](cudaError_t r) { if (r != cudaSuccess && r != cudaErrorNotReady && c.err == cudaSuccess) c.err = r; };
     note(cudaMemcpyAsync(c.d_jobs, c.h_jobs, sizeof(dm::HashJob) * c.njobs, cudaMemcpyHostToDevice, c.stream));
     note(cudaEventRecord(c.k_start, c.stream));
     if (c.err != cudaSuccess) { /* the job table may not be on the device: launching would run stale jobs */ }
@@ -945,7 +956,7 @@ void pump_main(dm_engine *e)
         while (b_live) {
             SlabBatch &b = e->batches[b_tail];
             bool done = true;
-            for (int i = 0; i < kCopyStreams; ++i) done = done && cudaEventQuery(b.ev[i]) == cudaSuccess;
+            for (int i = 0; i < kCopyStreams; ++i) done = done && poll_event(b.ev[i]) == cudaSuccess;
             if (!done) break;
             for (Slab *sl : b.slabs) slab_put(e, sl);
             b.slabs.clear(); b.busy = false;
@@ -960,7 +971,7 @@ void pump_main(dm_engine *e)
         bool reaped = false;
         for (Cycle &c : e->cycles)
             if (c.busy) {
-                const cudaError_t q = cudaEventQuery(c.k_end);
+                const cudaError_t q = poll_event(c.k_end);
                 if (q == cudaErrorNotReady) continue;
                 if (q != cudaSuccess && c.err == cudaSuccess) c.err = q;       // a faulted launch must end, not hang its streams
                 reap_cycle(e, c); --n_inflight; reaped = true;
@@ -2172,6 +2183,7 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
         for (uint32_t i = 0; i < n; ++i) e->ing_jobs_h[i] = tmp[order[i]];   // slot keeps the caller's index
     }
     cudaStream_t st = e->ingest_stream;
+    (void)cudaGetLastError();           // the caller's thread may carry a stale "not ready" from its own event polling
     cudaError_t err = cudaMemcpyAsync(e->ing_jobs_d, e->ing_jobs_h, sizeof(dm::HashJob) * (uint64_t)n, cudaMemcpyHostToDevice, st);
     if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev0, st);
     if (err == cudaSuccess)

@@ -574,6 +574,11 @@ __global__ void synth_fill_many_kernel(uint64_t seed, uint64_t first_blob, uint8
 
 static const FmaK kFmaK = {1u, 0xffffffffu, {0u, 0u}};
 
+// The launchers end in `return cudaGetLastError()`.  The runtime's per-thread last-error slot also holds
+// cudaErrorNotReady after a cudaEventQuery / cudaStreamQuery that was merely "not yet" (the pump polls events; a host
+// application such as PyTorch does too), so it is cleared first: what a launcher returns is about its own launch.
+static inline void clear_stale_error() { (void)cudaGetLastError(); }
+
 template <int kFma, int kStyle>
 static void launch_wide_t(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests, cudaStream_t stream)
 {
@@ -586,6 +591,7 @@ cudaError_t launch_sha256_wide(const HashJob *jobs, uint32_t njobs, uint32_t *st
                                cudaStream_t stream, int variant)
 {
     if (njobs == 0) return cudaSuccess;
+    clear_stale_error();
     switch (variant) {
 #define DM_W(f, st) case (f) + 4 * (st): launch_wide_t<f, st>(jobs, njobs, states, digests, stream); break;
     DM_W(0, 0) DM_W(1, 0) DM_W(2, 0) DM_W(0, 1) DM_W(1, 1) DM_W(2, 1)
@@ -602,6 +608,7 @@ cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *st
 {
     if (njobs == 0) return cudaSuccess;
     const uint32_t grid = (njobs + kDeepWarps - 1) / kDeepWarps;
+    clear_stale_error();
     switch (variant) {
     case 1: case 3: sha256_deep_kernel<1><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     case 2: sha256_deep_kernel<2><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
@@ -632,6 +639,7 @@ cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *s
                                 cudaStream_t stream, int streams_per_warp, int variant)
 {
     if (njobs == 0) return cudaSuccess;
+    clear_stale_error();
     return variant == 4 ? launch_group_t<4>(jobs, njobs, states, digests, stream, streams_per_warp)
                         : launch_group_t<0>(jobs, njobs, states, digests, stream, streams_per_warp);
 }
@@ -641,6 +649,7 @@ cudaError_t launch_synth_fill(uint64_t seed, uint64_t blob, uint64_t byte_off, v
 {
     if (len == 0) return cudaSuccess;
     size_t blocks = (len / 16 + 255) / 256;
+    clear_stale_error();
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 16) blocks = 148 * 16;
     synth_fill_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dm_blob_key(seed, blob), byte_off,
@@ -654,6 +663,7 @@ cudaError_t launch_synth_fill_many(uint64_t seed, uint64_t first_blob, void *bas
 {
     if (n == 0 || span == 0) return cudaSuccess;
     uint64_t blocks = (span / 16 + 255) / 256;
+    clear_stale_error();
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 16) blocks = 148 * 16;
     synth_fill_many_kernel<<<(unsigned)blocks, 256, 0, stream>>>(seed, first_blob, static_cast<uint8_t *>(base),

@@ -121,7 +121,11 @@ cudaError_t cudaDeviceSynchronize(void)
 }
 cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = 1ull << 30; return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t) { return "fake cuda error"; }
-cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+// The real runtime keeps a per-thread "last error" that cudaGetLastError returns and clears - and a query that says
+// "not ready" counts: cudaEventQuery / cudaStreamQuery leave cudaErrorNotReady there.  A launch wrapper that ends in
+// `return cudaGetLastError()` on a thread that polls events therefore reports a stale cudaErrorNotReady.
+static thread_local cudaError_t tl_last_error = cudaSuccess;
+cudaError_t cudaGetLastError(void) { const cudaError_t e = tl_last_error; tl_last_error = cudaSuccess; return e; }
 // Allocation registries, to model what the real runtime does with PAGEABLE host memory:
 //   cudaMemcpyAsync H2D  - the source is staged before the call returns (snapshot here), the device write is
 //                          stream-ordered;
@@ -248,7 +252,9 @@ cudaError_t cudaEventRecord(cudaEvent_t ev, cudaStream_t s)
 cudaError_t cudaEventQuery(cudaEvent_t ev)
 {
     std::lock_guard<std::mutex> g(ev->st->mu);
-    return ev->st->done >= ev->st->recorded ? cudaSuccess : cudaErrorNotReady;
+    if (ev->st->done >= ev->st->recorded) return cudaSuccess;
+    tl_last_error = cudaErrorNotReady;
+    return cudaErrorNotReady;
 }
 cudaError_t cudaEventSynchronize(cudaEvent_t ev)
 {
@@ -308,7 +314,7 @@ static cudaError_t run_all(const HashJob *jobs, uint32_t n, uint32_t *states, ui
 {
     if (inject_failure()) return cudaErrorUnknown;
     on_stream(st, [jobs, n, states, digests] { for (uint32_t i = 0; i < n; ++i) run_job(jobs[i], states, digests); });
-    return cudaSuccess;
+    return cudaGetLastError();                   // as the real launch wrappers end (sha256_kernels.cu)
 }
 cudaError_t launch_sha256_wide(const HashJob *j, uint32_t n, uint32_t *s, uint32_t *d, cudaStream_t st, int) { return run_all(j, n, s, d, st); }
 cudaError_t launch_sha256_deep(const HashJob *j, uint32_t n, uint32_t *s, uint32_t *d, cudaStream_t st, int) { return run_all(j, n, s, d, st); }
@@ -317,13 +323,13 @@ cudaError_t launch_sha256_group(const HashJob *j, uint32_t n, uint32_t *s, uint3
 cudaError_t launch_synth_fill(uint64_t seed, uint64_t blob, uint64_t off, void *dst, size_t len, cudaStream_t st)
 {
     on_stream(st, [=] { dmo_blob_fill(seed, blob, off, dst, len); });
-    return cudaSuccess;
+    return cudaGetLastError();
 }
 cudaError_t launch_synth_fill_many(uint64_t seed, uint64_t first, void *base, const uint64_t *offs, const uint64_t *lens,
                                    uint32_t n, uint64_t, uint64_t, cudaStream_t st)
 {
     on_stream(st, [=] { for (uint32_t i = 0; i < n; ++i) dmo_blob_fill(seed, first + i, 0, static_cast<uint8_t *>(base) + offs[i], lens[i]); });
-    return cudaSuccess;
+    return cudaGetLastError();
 }
 
 }  // namespace dm
