@@ -140,3 +140,25 @@ def test_python_mirror_gpu_test_logic_and_bench_flow_over_the_fake_runtime(tmp_p
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
     assert line["warmup"] >= 3 and line["gpu_launches"] > 0 and line["config"]["workload"] == "tiny"
     assert line["e2e"]["h2d_bytes_per_step"] == line["config"]["bytes_per_gpu_per_step"]
+
+
+def test_sass_timing_model_reproduces_the_measured_deep_kernel(tmp_path):
+    """tools/sass_sched.py on the built kernels: the shipped deep kernel's serial phase must come out at the measured
+    ~29 cycles per round (profiles/r01_sass_sched.txt), and the short-chain candidate must be predicted faster."""
+    import re
+    import shutil
+    import pytest
+    obj = os.path.join(ROOT, "demodel_b200", "csrc", "build", "sha256_kernels.o")
+    if not (shutil.which("cuobjdump") and os.path.exists(obj)):
+        pytest.skip("needs cuobjdump and the built kernel object")
+    sass = tmp_path / "all.sass"
+    with open(sass, "w") as f:
+        subprocess.run(["cuobjdump", "-sass", obj], stdout=f, check=True, timeout=300)
+    cyc = {}
+    for v in (0, 4):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_sched.py"), str(sass), f"deep_kernelILi{v}E"],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        cyc[v] = float(re.search(r"= ([0-9.]+) cycles per round", out.stdout).group(1))
+    assert 27.5 <= cyc[0] <= 30.5, cyc           # measured: 29.3
+    assert cyc[4] < cyc[0] - 2.0, cyc
