@@ -158,7 +158,11 @@ int dm_stream_flush(dm_engine *e, uint64_t id);
 /* Blocks until every byte is hashed.  digest_out receives the SHA-256 of
  * the bytes written.  *matched = 1 if expect was NULL or equals the digest
  * (the blob is then published in the CAS under digest_out), 0 otherwise (the
- * bytes are discarded).  The id is released either way. */
+ * bytes are discarded).  The id is released either way.
+ * Errors: DM_ESTATE (holes left by range parts), DM_ENOMEM, DM_ECUDA before the
+ * final hash was started leave the stream open - call dm_stream_abort.  DM_ECUDA
+ * after it (a copy or launch failed while the body was being hashed): *matched = 0,
+ * nothing was cached, the id is released. */
 int dm_stream_finish(dm_engine *e, uint64_t id, uint8_t digest_out[32], int *matched);
 /* Upstream error / client went away: drop the partial blob, release the id. */
 int dm_stream_abort(dm_engine *e, uint64_t id);
