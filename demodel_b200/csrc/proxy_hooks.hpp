@@ -121,6 +121,7 @@ private:
         eof_ = true;
         open_ = false;
         rc_ = dm_stream_finish(e_, id_, digest_, &matched_);
+        if (rc_ != DM_OK) dm_stream_abort(e_, id_);     // some failures leave the stream open; a released id just says so (ids are never reused)
         return rc_;
     }
     void Abort()

@@ -211,6 +211,7 @@ func (t *BodyTee) finish() error {
 	t.open = false
 	var m C.int
 	if err := check(C.dm_stream_finish(t.e, t.id, (*C.uint8_t)(unsafe.Pointer(&t.Digest[0])), &m)); err != nil {
+		C.dm_stream_abort(t.e, t.id) // some failures leave the stream open; a released id just says so (ids are never reused)
 		return err
 	}
 	t.Matched = m != 0
