@@ -148,7 +148,14 @@ class Engine:
         except Exception:
             self.stream_abort(sid)
             raise
-        return self.stream_finish(sid)
+        try:
+            return self.stream_finish(sid)
+        except DmError:
+            try:
+                self.stream_abort(sid)        # some failures leave the stream open; a released id just says so
+            except DmError:
+                pass
+            raise
 
     # -- hit serving (OnRequest short-circuit) --------------------------------
     def cache_contains(self, digest: bytes) -> Optional[int]:
