@@ -1,0 +1,513 @@
+// C-ABI, part 2: hit serving (readers, followers), device-resident ingest, the synthetic generator.
+#include "engine_internal.hpp"
+
+extern "C" {
+
+// ---- hit serving ---------------------------------------------------------------
+
+int dm_cache_contains(dm_engine *e, const uint8_t digest[32], uint64_t *size)
+{
+    if (!e || !digest) return fail(DM_EINVAL, "null argument");
+    Digest d;
+    memcpy(d.b, digest, 32);
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        auto it = e->blobs.find(d);
+        if (it != e->blobs.end() && (it->second->in_hbm || it->second->on_disk)) {
+            if (size) *size = it->second->size;
+            return DM_OK;
+        }
+    }
+    if (!e->cas_dir.empty()) {
+        struct stat st;
+        if (stat(blob_path(e, digest).c_str(), &st) == 0) { if (size) *size = (uint64_t)st.st_size; return DM_OK; }
+    }
+    return DM_ENOENT;
+}
+
+int dm_cache_open(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size)
+{
+    if (!e || !digest || !reader) return fail(DM_EINVAL, "null argument");
+    Digest d;
+    memcpy(d.b, digest, 32);
+    auto r = std::make_shared<Reader>();
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        auto it = e->blobs.find(d);
+        if (it != e->blobs.end() && it->second->in_hbm) {
+            r->blob = it->second;
+            r->blob->readers++;
+            r->blob->tick = ++e->tick;
+            r->size = r->blob->size;
+        }
+    }
+    if (!r->blob) {
+        if (e->cas_dir.empty()) return DM_ENOENT;
+        r->fd = open(blob_path(e, digest).c_str(), O_RDONLY);
+        if (r->fd < 0) return DM_ENOENT;
+        struct stat st;
+        fstat(r->fd, &st);
+        r->size = (uint64_t)st.st_size;
+        if (FILE *mf = fopen((blob_path(e, digest) + ".meta").c_str(), "r")) {
+            char tmp[4096];
+            size_t k;
+            while ((k = fread(tmp, 1, sizeof tmp, mf)) > 0) r->disk_meta.append(tmp, k);
+            fclose(mf);
+        }
+    }
+    uint64_t id;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        id = e->next_id++;
+    }
+    {
+        std::lock_guard<std::mutex> g(e->reader_mu[id % kStripes]);
+        e->readers[id % kStripes][id] = r;
+    }
+    *reader = id;
+    if (size) *size = r->size;
+    return DM_OK;
+}
+
+static std::shared_ptr<Reader> find_reader(dm_engine *e, uint64_t id)
+{
+    std::lock_guard<std::mutex> g(e->reader_mu[id % kStripes]);
+    auto it = e->readers[id % kStripes].find(id);
+    return it == e->readers[id % kStripes].end() ? nullptr : it->second;
+}
+
+// Read from a body that is still arriving (request coalescing).  Blocks until bytes past `off` have
+// been DMA'd, the body completes, or it fails.  Returns DM_OK with *nread set, a dm_err, or 1 when the
+// body has completed and been published (the reader has been switched to the blob; caller continues).
+static int follow_read(dm_engine *e, Reader *r, uint64_t off, void *buf, size_t len, size_t *nread)
+{
+    std::lock_guard<std::mutex> gr(r->mu);
+    if (!r->follow) return 1;
+    Stream *s = r->follow.get();
+    std::vector<std::pair<uint8_t *, uint64_t>> segs;
+    size_t n = 0;
+    {
+        std::unique_lock<std::mutex> g(s->mu);
+        s->followers++;
+        s->cv.wait(g, [&] {
+            return s->st == St::Done || s->st == St::Aborted || (off < s->dma_issued && !s->completing) || len == 0;
+        });
+        s->followers--;
+        if (s->st == St::Aborted) return fail(DM_ESTATE, "the upstream body this reader followed was aborted");
+        if (s->st == St::Done) {
+            std::shared_ptr<Blob> b = s->blob;
+            g.unlock();
+            if (!b) return fail(DM_ESTATE, "the upstream body this reader followed failed verification");
+            std::lock_guard<std::mutex> g2(e->mu);
+            if (!b->in_hbm) return fail(DM_ENOENT, "blob evicted before the follower switched over");
+            b->readers++;
+            r->blob = b;
+            r->size = b->size;
+            r->follow.reset();
+            return 1;
+        }
+        if (len == 0) return DM_OK;
+        n = (size_t)std::min<uint64_t>(len, s->dma_issued - off);
+        for_segments(e, s->extents, off, n, [&](uint8_t *dev, uint64_t l) { segs.emplace_back(dev, l); });
+        s->follow_reads++;                      // pins the extents until the copy-out below is done
+    }
+    struct Unpin {
+        Stream *s;
+        ~Unpin() { { std::lock_guard<std::mutex> g(s->mu); s->follow_reads--; } s->cv.notify_all(); }
+    } unpin{s};
+    // the bytes may still be in flight on the body's copy stream: order the read-back after them
+    cudaSetDevice(e->device);
+    Bounce *bn = bounce_get(e);
+    cudaEvent_t ev;
+    cudaError_t err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventRecord(ev, e->copy_stream[s->id % kCopyStreams]);
+    if (err == cudaSuccess) err = cudaStreamWaitEvent(bn->stream, ev, 0);
+    uint8_t *out = static_cast<uint8_t *>(buf);
+    size_t done = 0;
+    for (auto &sg : segs) {
+        uint64_t left = sg.second;
+        uint8_t *dev = sg.first;
+        while (left && err == cudaSuccess) {
+            const size_t m = (size_t)std::min<uint64_t>(left, kBounceBytes);
+            err = cudaMemcpyAsync(bn->host, dev, m, cudaMemcpyDeviceToHost, bn->stream);
+            if (err == cudaSuccess) err = cudaStreamSynchronize(bn->stream);
+            if (err == cudaSuccess) memcpy(out + done, bn->host, m);
+            done += m; dev += m; left -= m;
+        }
+    }
+    if (ev) cudaEventDestroy(ev);
+    bounce_put(e, bn);
+    if (err != cudaSuccess) return fail_cuda(err, "follow_read D2H");
+    e->st_d2h += done; e->st_served += done;
+    if (nread) *nread = done;
+    return DM_OK;
+}
+
+// Start the D2H of [start, start + <=4 MiB) of the blob into a read-ahead window.
+static cudaError_t window_fill(dm_engine *e, Reader *r, Window &w, uint64_t start)
+{
+    const uint64_t n = std::min<uint64_t>(kBounceBytes, r->size - start);
+    uint8_t *dst = w.b->host;
+    cudaError_t err = cudaSuccess;
+    for_segments(e, r->blob->extents, start, n, [&](uint8_t *dev, uint64_t l) {
+        if (err == cudaSuccess) err = cudaMemcpyAsync(dst, dev, l, cudaMemcpyDeviceToHost, w.b->stream);
+        dst += l;
+    });
+    w.off = start; w.len = n; w.pending = true;
+    e->st_d2h += n;
+    return err;
+}
+
+int dm_cache_read(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t len, size_t *nread)
+{
+    if (!e || (!buf && len)) return fail(DM_EINVAL, "null argument");
+    std::shared_ptr<Reader> r = find_reader(e, reader);
+    if (!r) return fail(DM_EINVAL, "unknown reader id");
+    if (nread) *nread = 0;
+    if (r->follow) {
+        int rc = follow_read(e, r.get(), off, buf, len, nread);
+        if (rc != 1) return rc;                 // 1: the body completed and was published: fall through to the blob
+    }
+    if (off > r->size) return fail(DM_ERANGE, "offset beyond blob end");
+    len = (size_t)std::min<uint64_t>(len, r->size - off);
+    if (len == 0) return DM_OK;
+    uint8_t *out = static_cast<uint8_t *>(buf);
+    if (!r->blob) {
+        size_t got = 0;
+        while (got < len) {
+            ssize_t n = pread(r->fd, out + got, len - got, (off_t)(off + got));
+            if (n < 0) { if (errno == EINTR) continue; return fail(DM_EIO, "pread failed"); }
+            if (n == 0) break;
+            got += (size_t)n;
+        }
+        if (nread) *nread = got;
+        e->st_served += got;
+        return DM_OK;
+    }
+    cudaSetDevice(e->device);
+    std::lock_guard<std::mutex> g(r->mu);
+    if (!r->tried_windows) {
+        r->tried_windows = true;
+        Bounce *a = bounce_try_get(e), *b = a ? bounce_try_get(e) : nullptr;
+        if (a && b) { r->win[0].b = a; r->win[1].b = b; }
+        else if (a) bounce_put(e, a);
+    }
+    size_t done = 0;
+    int rc = DM_OK;
+    if (r->win[0].b) {
+        // HTTP bodies are read front to back in small pieces (io.Copy: 32 KiB): serve them from two
+        // 4 MiB pinned windows, the next one filling by DMA while this one is copied out.
+        while (done < len) {
+            const uint64_t pos = off + done;
+            Window *w = nullptr;
+            for (Window &c : r->win) if (c.len && pos >= c.off && pos < c.off + c.len) w = &c;
+            cudaError_t err = cudaSuccess;
+            if (!w) {                                              // miss: restart the pipeline at pos
+                for (Window &c : r->win) if (c.pending) { cudaStreamSynchronize(c.b->stream); c.pending = false; }
+                err = window_fill(e, r.get(), r->win[0], pos);
+                r->win[1].len = 0;
+                if (err == cudaSuccess && pos + r->win[0].len < r->size)
+                    err = window_fill(e, r.get(), r->win[1], pos + r->win[0].len);
+                if (err != cudaSuccess) { rc = fail_cuda(err, "cudaMemcpyAsync(D2H)"); break; }
+                w = &r->win[0];
+            }
+            if (w->pending) {
+                err = cudaStreamSynchronize(w->b->stream);
+                w->pending = false;
+                if (err != cudaSuccess) { rc = fail_cuda(err, "cudaStreamSynchronize(D2H)"); break; }
+            }
+            const size_t n = (size_t)std::min<uint64_t>(len - done, w->off + w->len - pos);
+            memcpy(out + done, w->b->host + (pos - w->off), n);
+            done += n;
+            if (pos + n == w->off + w->len) {                      // window drained: refill it behind the other one
+                Window &other = (w == &r->win[0]) ? r->win[1] : r->win[0];
+                const uint64_t next = other.len ? other.off + other.len : w->off + w->len;
+                if (next < r->size && other.len && other.off == w->off + w->len) {
+                    err = window_fill(e, r.get(), *w, next);
+                    if (err != cudaSuccess) { rc = fail_cuda(err, "cudaMemcpyAsync(D2H)"); break; }
+                } else w->len = 0;
+            }
+        }
+    } else {
+        Bounce *bn = bounce_get(e);                                // no windows left: one-shot staging
+        while (done < len) {
+            const size_t n = std::min(len - done, kBounceBytes);
+            uint8_t *dst = bn->host;
+            cudaError_t err = cudaSuccess;
+            for_segments(e, r->blob->extents, off + done, n, [&](uint8_t *dev, uint64_t l) {
+                if (err == cudaSuccess) err = cudaMemcpyAsync(dst, dev, l, cudaMemcpyDeviceToHost, bn->stream);
+                dst += l;
+            });
+            if (err == cudaSuccess) err = cudaStreamSynchronize(bn->stream);
+            if (err != cudaSuccess) { rc = fail_cuda(err, "cudaMemcpyAsync(D2H)"); break; }
+            memcpy(out + done, bn->host, n);
+            done += n;
+            e->st_d2h += n;
+        }
+        bounce_put(e, bn);
+    }
+    e->st_served.fetch_add(done, std::memory_order_relaxed);
+    if (nread) *nread = done;
+    return rc;
+}
+
+int dm_cache_meta(dm_engine *e, uint64_t reader, char *buf, size_t cap, size_t *len)
+{
+    if (!e || !len || (!buf && cap)) return fail(DM_EINVAL, "null argument");
+    std::shared_ptr<Reader> r = find_reader(e, reader);
+    if (!r) return fail(DM_EINVAL, "unknown reader id");
+    std::string j;
+    if (r->blob) {
+        std::lock_guard<std::mutex> g(e->mu);
+        j = sidecar_json(*r->blob);
+    } else j = r->disk_meta;
+    *len = j.size();
+    if (cap) {
+        const size_t n = std::min(cap - 1, j.size());
+        memcpy(buf, j.data(), n);
+        buf[n] = 0;
+    }
+    return DM_OK;
+}
+
+int dm_cache_close(dm_engine *e, uint64_t reader)
+{
+    if (!e) return fail(DM_EINVAL, "null argument");
+    std::shared_ptr<Reader> r;
+    {
+        std::lock_guard<std::mutex> g(e->reader_mu[reader % kStripes]);
+        auto it = e->readers[reader % kStripes].find(reader);
+        if (it == e->readers[reader % kStripes].end()) return fail(DM_EINVAL, "unknown reader id");
+        r = it->second;
+        e->readers[reader % kStripes].erase(it);
+    }
+    {
+        std::lock_guard<std::mutex> g(r->mu);
+        for (Window &w : r->win) {
+            if (!w.b) continue;
+            if (w.pending) cudaStreamSynchronize(w.b->stream);
+            bounce_put(e, w.b);
+            w.b = nullptr;
+        }
+    }
+    if (r->blob) {
+        std::lock_guard<std::mutex> g(e->mu);
+        r->blob->readers--;
+    }
+    if (r->fd >= 0) close(r->fd);
+    return DM_OK;
+}
+
+int dm_cache_follow(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size_hint)
+{
+    if (!e || !digest || !reader) return fail(DM_EINVAL, "null argument");
+    Digest d;
+    memcpy(d.b, digest, 32);
+    auto r = std::make_shared<Reader>();
+    uint64_t id;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        auto it = e->inflight.find(d);
+        if (it == e->inflight.end()) return DM_ENOENT;
+        r->follow = it->second.lock();
+        if (!r->follow) { e->inflight.erase(it); return DM_ENOENT; }
+        id = e->next_id++;
+    }
+    r->size = r->follow->size_hint;
+    {
+        std::lock_guard<std::mutex> g(e->reader_mu[id % kStripes]);
+        e->readers[id % kStripes][id] = r;
+    }
+    *reader = id;
+    if (size_hint) *size_hint = r->size;
+    return DM_OK;
+}
+
+int dm_cache_evict(dm_engine *e, const uint8_t digest[32])
+{
+    if (!e || !digest) return fail(DM_EINVAL, "null argument");
+    Digest d;
+    memcpy(d.b, digest, 32);
+    std::shared_ptr<Blob> b;
+    std::vector<Extent> ext;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        auto it = e->blobs.find(d);
+        if (it == e->blobs.end() || !it->second->in_hbm) return DM_ENOENT;
+        if (it->second->readers) return fail(DM_ESTATE, "blob has open readers");
+        b = it->second;
+        b->in_hbm = false;
+        ext.swap(b->extents);                       // under the lock (see evict_for)
+        if (!b->on_disk) e->blobs.erase(it);
+    }
+    free_extents(e, ext);
+    return DM_OK;
+}
+
+int dm_cache_device_extents(dm_engine *e, uint64_t reader, void **dev_ptrs, uint64_t *lens, uint32_t max_ext)
+{
+    if (!e) return fail(DM_EINVAL, "null argument");
+    std::shared_ptr<Reader> r = find_reader(e, reader);
+    if (!r) return fail(DM_EINVAL, "unknown reader id");
+    if (!r->blob) return fail(DM_ESTATE, "blob is on the disk tier only");
+    const auto &ext = r->blob->extents;
+    uint64_t left = r->blob->size;
+    for (uint32_t i = 0; i < ext.size() && i < max_ext; ++i) {
+        if (dev_ptrs) dev_ptrs[i] = e->arena_base + ext[i].off;
+        if (lens) lens[i] = std::min(left, ext[i].len);
+        left -= std::min(left, ext[i].len);
+    }
+    return (int)ext.size();
+}
+
+// ---- device-resident ingest -------------------------------------------------------
+
+int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets, const uint64_t *lengths,
+                     uint32_t n, const uint8_t *expect, uint8_t *digests_out, uint8_t *matched_out,
+                     uint32_t flags, double *kernel_ms)
+{
+    if (!e || ((!offsets || !lengths || !dev_base) && n)) return fail(DM_EINVAL, "null argument");
+    if (kernel_ms) *kernel_ms = 0.0;
+    if (n == 0) return DM_OK;
+    if (((uintptr_t)dev_base) & 15) return fail(DM_EINVAL, "dev_base must be 16-byte aligned");
+    for (uint32_t i = 0; i < n; ++i)
+        if (offsets[i] & 15) return fail(DM_EINVAL, "offsets must be multiples of 16");
+    cudaSetDevice(e->device);
+    std::lock_guard<std::mutex> gi(e->ingest_mu);
+    int rc = ensure_ingest_scratch(e, n);
+    if (rc != DM_OK) return rc;
+    const bool hash_only = (flags & DM_ING_HASH_ONLY) != 0;
+    std::vector<Extent> ext(hash_only ? 0 : n, Extent{0, 0});
+    auto cleanup = [&] {
+        std::lock_guard<std::mutex> g(e->arena_mu);
+        for (const Extent &x : ext) e->arena.release(x.off, x.len);
+    };
+    if ((flags & DM_ING_REPLACE) && expect && !hash_only) evict_many(e, expect, n);
+    const uint8_t *base = static_cast<const uint8_t *>(dev_base);
+    uint64_t total = 0;
+    uint32_t allocated = 0;
+    if (!hash_only) {                                   // fast path: all extents under one arena lock
+        std::lock_guard<std::mutex> g(e->arena_mu);
+        for (; allocated < n; ++allocated) {
+            const uint64_t want = round_up(std::max<uint64_t>(lengths[allocated], 1), kAlign);
+            uint64_t off;
+            if (!e->arena.alloc(want, &off)) break;
+            ext[allocated] = Extent{off, want};
+        }
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t len = lengths[i];
+        dm::HashJob &jb = e->ing_jobs_h[i];
+        jb.src = base + offsets[i]; jb.dst = nullptr; jb.nbytes = len; jb.total_len = len;
+        jb.slot = i; jb.flags = dm::JOB_INIT | dm::JOB_FINAL; jb.one = 1; jb.pad_ = 0;
+        if (!hash_only) {
+            if (i >= allocated) {                       // arena full: evict LRU blobs one allocation at a time
+                Extent x;
+                if (!arena_alloc(e, len, &x)) { cleanup(); return fail(DM_ENOMEM, "HBM CAS arena exhausted"); }
+                ext[i] = x;
+            }
+            jb.dst = e->arena_base + ext[i].off;
+        }
+        total += len;
+    }
+    int spw = e->force_spw ? e->force_spw : dm::streams_per_warp_for(n);
+    if (flags & DM_ING_FORCE_WIDE) spw = 32;
+    if (flags & DM_ING_FORCE_DEEP) spw = 1;
+    if (flags & DM_ING_SPW_MASK) spw = 1 << (((flags & DM_ING_SPW_MASK) >> DM_ING_SPW_SHIFT) - 1);
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    if (spw > 1) {
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            return e->ing_jobs_h[a].nbytes > e->ing_jobs_h[b].nbytes; });
+        std::vector<dm::HashJob> tmp(e->ing_jobs_h, e->ing_jobs_h + n);
+        for (uint32_t i = 0; i < n; ++i) e->ing_jobs_h[i] = tmp[order[i]];   // slot keeps the caller's index
+    }
+    cudaStream_t st = e->ingest_stream;
+    (void)cudaGetLastError();           // the caller's thread may carry a stale "not ready" from its own event polling
+    cudaError_t err = cudaMemcpyAsync(e->ing_jobs_d, e->ing_jobs_h, sizeof(dm::HashJob) * (uint64_t)n, cudaMemcpyHostToDevice, st);
+    if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev0, st);
+    if (err == cudaSuccess)
+        err = spw == 1 ? dm::launch_sha256_deep(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, e->variant_deep)
+            : spw == 32 ? dm::launch_sha256_wide(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, e->variant_wide)
+                        : dm::launch_sha256_group(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, spw, e->variant_deep);
+    if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev1, st);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(e->ing_digests_h, e->ing_digests, 32ull * n, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) {
+        cudaStreamSynchronize(st);      // whatever was enqueued before the failure still uses the job table and the extents
+        cleanup();
+        return fail_cuda(err, "dm_ingest_device launch");
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->ing_ev0, e->ing_ev1);
+    if (kernel_ms) *kernel_ms = ms;
+    { std::lock_guard<std::mutex> g(e->stat_mu); e->st_kernel_ms += ms; }
+    e->st_launches++; (spw == 1 ? e->st_deep : spw == 32 ? e->st_wide : e->st_group)++;
+    e->st_hashed += total;
+    std::vector<Verified> good;
+    std::vector<Extent> bad;
+    if (!hash_only) good.reserve(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        Digest d;
+        words_to_digest(e->ing_digests_h + 8ull * i, d.b);
+        if (digests_out) memcpy(digests_out + 32ull * i, d.b, 32);
+        const int ok = (!expect || memcmp(expect + 32ull * i, d.b, 32) == 0) ? 1 : 0;
+        if (matched_out) matched_out[i] = (uint8_t)ok;
+        if (hash_only) continue;
+        if (ok) good.push_back(Verified{d, lengths[i], ext[i]});
+        else { bad.push_back(ext[i]); e->st_mismatch++; }
+    }
+    if (!good.empty()) publish_many(e, good);
+    if (!bad.empty()) {
+        std::lock_guard<std::mutex> g(e->arena_mu);
+        for (const Extent &x : bad) e->arena.release(x.off, x.len);
+    }
+    return DM_OK;
+}
+
+// ---- synthetic bytes ---------------------------------------------------------------
+
+void dm_synth_fill_host(uint64_t seed, uint64_t blob, uint64_t byte_off, void *dst, size_t len)
+{
+    const uint64_t key = dm_blob_key(seed, blob);
+    uint8_t *p = static_cast<uint8_t *>(dst);
+    uint64_t j = byte_off;
+    while (len && (j & 7)) { *p++ = (uint8_t)(dm_blob_word_k(key, j >> 3) >> (8 * (j & 7))); ++j; --len; }
+    while (len >= 8) { const uint64_t w = dm_blob_word_k(key, j >> 3); memcpy(p, &w, 8); p += 8; j += 8; len -= 8; }
+    while (len) { *p++ = (uint8_t)(dm_blob_word_k(key, j >> 3) >> (8 * (j & 7))); ++j; --len; }
+}
+
+int dm_synth_fill_device(dm_engine *e, uint64_t seed, uint64_t blob, uint64_t byte_off, void *dev_dst, size_t len)
+{
+    if (!e || (!dev_dst && len)) return fail(DM_EINVAL, "null argument");
+    cudaSetDevice(e->device);
+    CU_TRY(dm::launch_synth_fill(seed, blob, byte_off, dev_dst, len, e->util_stream));
+    CU_TRY(cudaStreamSynchronize(e->util_stream));
+    return DM_OK;
+}
+
+int dm_synth_fill_device_many(dm_engine *e, uint64_t seed, uint64_t first_blob, void *dev_base,
+                              const uint64_t *offsets, const uint64_t *lengths, uint32_t n)
+{
+    if (!e || ((!offsets || !lengths || !dev_base) && n)) return fail(DM_EINVAL, "null argument");
+    if (n == 0) return DM_OK;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (offsets[i] & 15) return fail(DM_EINVAL, "offsets must be multiples of 16");
+        if (i && offsets[i] < offsets[i - 1] + lengths[i - 1]) return fail(DM_EINVAL, "blobs must be ascending and disjoint");
+    }
+    cudaSetDevice(e->device);
+    uint64_t *d_tab = nullptr;
+    CU_TRY(cudaMalloc(&d_tab, 16ull * n));
+    cudaError_t err = cudaMemcpyAsync(d_tab, offsets, 8ull * n, cudaMemcpyHostToDevice, e->util_stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d_tab + n, lengths, 8ull * n, cudaMemcpyHostToDevice, e->util_stream);
+    if (err == cudaSuccess)
+        err = dm::launch_synth_fill_many(seed, first_blob, dev_base, d_tab, d_tab + n, n, offsets[0],
+                                         offsets[n - 1] + lengths[n - 1] - offsets[0], e->util_stream);
+    const cudaError_t sync = cudaStreamSynchronize(e->util_stream);     // also on failure: the table may still be in use
+    if (err == cudaSuccess) err = sync;
+    cudaFree(d_tab);
+    if (err != cudaSuccess) return fail_cuda(err, "dm_synth_fill_device_many");
+    return DM_OK;
+}
+
+}  // extern "C"

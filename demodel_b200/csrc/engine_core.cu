@@ -1,0 +1,904 @@
+// The blob hash-and-cache engine behind include/demodel_b200.h.
+//
+// Data path:
+//
+//   dm_stream_write ──memcpy──▶ pinned ring slab ──one H2D DMA per slab──▶ the blob's
+//   (many threads)              (per stream)        (copy streams)         CAS extent in HBM
+//                                                                               │
+//   pump thread: gathers the streams with unhashed bytes into a job table       ▼
+//   (one slab-sized job per stream, at most one in flight per stream) and  sha256_{deep,group,wide}
+//   launches ONE multi-buffer SHA-256 kernel over them; up to 8 launches   (reads each byte once)
+//   overlap on separate CUDA streams, each ordered after the DMAs by an
+//   event.  Finished streams get their digest through mapped pinned memory,
+//   are compared with the expected oid and published in the CAS index; spill
+//   threads write published blobs to the disk tier with D2H copies on side
+//   streams; readers (hits, followers of in-flight bodies) copy out through
+//   pinned read-ahead windows.
+//
+// The bytes land at their final CAS address straight from the DMA, so the
+// ring path costs HBM one write (DMA) + one read (hash) per blob byte.  The
+// device-resident path (dm_ingest_device) fuses the copy into the hash kernel.
+//
+// Lock order (outer → inner): reader.mu → stream.mu → {arena_mu, e->mu, work_mu};
+// slab_mu → work_mu; stripe / reader-stripe mutexes are leaves taken alone.
+// The pump never holds work_mu while taking a stream mutex.
+//
+// Reference hooks served: cmd/demodel/start.go:201-204 (ingest) and
+// start.go:197-200 (hit serving); see include/demodel_b200.h.
+#include "engine_internal.hpp"
+
+namespace dmi {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *what)
+{
+    g_last_error = what ? what : "";
+    return code;
+}
+// cudaEventQuery's "not ready" also lands in the runtime's per-thread last-error slot, where the next
+// `cudaGetLastError()` (the launch wrappers end in one) would find it and report a launch failure that never
+// happened.  Every poll goes through here.
+cudaError_t poll_event(cudaEvent_t ev)
+{
+    const cudaError_t q = cudaEventQuery(ev);
+    if (q == cudaErrorNotReady) (void)cudaGetLastError();
+    return q;
+}
+
+int fail_cuda(cudaError_t err, const char *where)
+{
+    g_last_error = std::string(where) + ": " + cudaGetErrorString(err);
+    return DM_ECUDA;
+}
+
+
+// ---- extents ---------------------------------------------------------------
+
+// Device pointer of byte `off`, and how many bytes are contiguous from there.
+uint8_t *seg_at(dm_engine *e, const std::vector<Extent> &ext, uint64_t off, uint64_t *contig)
+{
+    uint64_t base = 0;
+    for (const Extent &x : ext) {
+        if (off < base + x.len) { *contig = base + x.len - off; return e->arena_base + x.off + (off - base); }
+        base += x.len;
+    }
+    *contig = 0;
+    return nullptr;
+}
+
+void free_extents(dm_engine *e, std::vector<Extent> &ext)
+{
+    std::lock_guard<std::mutex> g(e->arena_mu);
+    for (const Extent &x : ext) e->arena.release(x.off, x.len);
+    ext.clear();
+}
+
+// Evict least-recently-used unreferenced blobs until `need` bytes could fit.
+// Caller holds neither e->mu nor arena_mu.
+bool evict_for(dm_engine *e, uint64_t need)
+{
+    for (;;) {
+        std::shared_ptr<Blob> victim;
+        std::vector<Extent> ext;
+        {
+            std::lock_guard<std::mutex> g(e->mu);
+            for (auto &kv : e->blobs) {
+                Blob *b = kv.second.get();
+                if (!b->in_hbm || b->readers) continue;
+                if (!e->cas_dir.empty() && !b->spill_done) continue;   // not yet safe on disk
+                if (!victim || b->tick < victim->tick) victim = kv.second;
+            }
+            if (!victim) return false;
+            victim->in_hbm = false;
+            ext.swap(victim->extents);          // taken under the lock: a re-publish may install new ones at once
+            if (!victim->on_disk) e->blobs.erase(victim->digest);
+        }
+        free_extents(e, ext);
+        std::lock_guard<std::mutex> g(e->arena_mu);
+        uint64_t off;
+        if (e->arena.alloc(need, &off)) { e->arena.release(off, need); return true; }
+    }
+}
+
+bool arena_alloc(dm_engine *e, uint64_t len, Extent *out)
+{
+    len = round_up(std::max<uint64_t>(len, 1), kAlign);
+    for (int attempt = 0; attempt < 4; ++attempt) {      // another thread may take what an eviction freed
+        {
+            std::lock_guard<std::mutex> g(e->arena_mu);
+            uint64_t off;
+            if (e->arena.alloc(len, &off)) { out->off = off; out->len = len; return true; }
+        }
+        if (!evict_for(e, len)) return false;
+    }
+    return false;
+}
+
+// Make sure the stream's extents cover `need` bytes.  Stream mutex held.
+int ensure_capacity(dm_engine *e, Stream *s, uint64_t need)
+{
+    while (s->capacity < need) {
+        uint64_t want = need - s->capacity;
+        if (!s->extents.empty()) {   // unknown / exceeded size: grow geometrically
+            const uint64_t grow = std::min<uint64_t>(std::max<uint64_t>(s->capacity, e->cfg.slab_bytes), kMaxGrow);
+            want = std::max(want, grow);
+        }
+        Extent x;
+        if (!arena_alloc(e, want, &x)) {
+            if (!arena_alloc(e, need - s->capacity, &x)) return fail(DM_ENOMEM, "HBM CAS arena exhausted");
+        }
+        s->extents.push_back(x);
+        s->capacity += x.len;
+    }
+    return DM_OK;
+}
+
+// ---- ring slabs --------------------------------------------------------------
+
+Slab *slab_get(dm_engine *e)
+{
+    std::unique_lock<std::mutex> g(e->slab_mu);
+    if (e->slab_free.empty() && !e->stop) {
+        e->st_ring_waits++;
+        // Every slab is out: some are only partly filled and held by streams waiting for their next
+        // bytes.  Ask the pump to DMA those early so they recycle (otherwise more live streams than
+        // slabs would starve — or, with one thread driving many streams, deadlock).
+        { std::lock_guard<std::mutex> gw(e->work_mu); e->ring_starved.store(true); }   // under the pump's mutex: no lost wake-up
+        e->work_cv.notify_one();
+    }
+    e->ring_waiters++;
+    e->slab_cv.wait(g, [&] { return !e->slab_free.empty() || e->stop; });
+    e->ring_waiters--;
+    if (e->slab_free.empty()) return nullptr;
+    Slab *s = e->slab_free.back();
+    e->slab_free.pop_back();
+    return s;
+}
+
+void slab_put(dm_engine *e, Slab *s)
+{
+    {
+        std::lock_guard<std::mutex> g(e->slab_mu);
+        e->slab_free.push_back(s);
+    }
+    e->slab_cv.notify_one();
+}
+
+// Give the stream a fresh slab.  The stream mutex is dropped while waiting for
+// ring back-pressure: the pump needs it to build jobs, and only the pump's
+// reaping frees slabs.
+int take_slab(dm_engine *e, Stream *s, std::unique_lock<std::mutex> &g)
+{
+    g.unlock();
+    Slab *fresh = slab_get(e);
+    g.lock();
+    if (!fresh) return fail(DM_ESTATE, "engine stopping");
+    if (s->st != St::Open) { slab_put(e, fresh); return fail(DM_ESTATE, "stream closed while waiting for the ring"); }
+    if (s->cur) { slab_put(e, fresh); return DM_OK; }
+    s->cur = fresh;
+    s->cur_fill = s->carry_fill;
+    if (s->carry_fill) { memcpy(fresh->host, s->carry, s->carry_fill); s->carry_fill = 0; }
+    return DM_OK;
+}
+
+// Tell the pump this stream has new DMA'd bytes (or is finishing).  Stream mutex held.
+void mark_dirty(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *submitted)
+{
+    const bool enqueue = !sp->queued;
+    sp->queued = true;
+    {
+        std::lock_guard<std::mutex> g(e->work_mu);
+        if (submitted) e->pending_slabs.push_back(submitted);
+        if (enqueue) e->dirty.push_back(sp);
+    }
+    e->work_cv.notify_one();
+}
+
+// DMA `n` staged bytes to blob offset `base`.  Stream mutex held.  The slab is handed to the pump
+// (released once its copy event completes) on success, returned to the ring on failure.
+int dma_range(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *slab, uint64_t base, uint32_t n)
+{
+    Stream *s = sp.get();
+    cudaSetDevice(e->device);       // the caller may be any OS thread (cgo)
+    int rc = ensure_capacity(e, s, base + n);
+    if (rc != DM_OK) { slab_put(e, slab); return rc; }
+    cudaStream_t cs = e->copy_stream[s->id % kCopyStreams];
+    const uint8_t *src = slab->host;
+    cudaError_t err = cudaSuccess;
+    for_segments(e, s->extents, base, n, [&](uint8_t *dev, uint64_t len) {
+        if (err == cudaSuccess) err = cudaMemcpyAsync(dev, src, len, cudaMemcpyHostToDevice, cs);
+        src += len;
+    });
+    if (err != cudaSuccess) { s->cuda_failed = true; slab_put(e, slab); return fail_cuda(err, "cudaMemcpyAsync(H2D slab)"); }
+    e->st_h2d += n;
+    return DM_OK;
+}
+
+// The contiguous frontier swallows islands that now touch it.  Stream mutex held.
+void absorb_islands(Stream *s)
+{
+    if (s->cur_fill) return;            // staged sequential bytes sit between the frontier and any island
+    auto it = s->islands.begin();
+    while (it != s->islands.end() && it->first <= s->dma_issued) {
+        s->dma_issued = std::max(s->dma_issued, it->second);
+        it = s->islands.erase(it);
+    }
+}
+
+// DMA the stream's sequential slab to its place in the blob.  Stream mutex held.
+int submit_slab(dm_engine *e, const std::shared_ptr<Stream> &sp)
+{
+    Stream *s = sp.get();
+    if (!s->cur) return DM_OK;
+    Slab *slab = s->cur;
+    const uint32_t n = s->cur_fill;
+    s->cur = nullptr; s->cur_fill = 0;
+    if (n == 0) { slab_put(e, slab); return DM_OK; }
+    e->st_ingested.fetch_add(n, std::memory_order_relaxed);       // per slab, not per write: one shared line, many writer threads
+    if (s->verify_only) {
+        cudaSetDevice(e->device);
+        cudaError_t err = cudaMemcpyAsync(slab->dev, slab->host, n, cudaMemcpyHostToDevice, e->copy_stream[s->id % kCopyStreams]);
+        if (err != cudaSuccess) { slab_put(e, slab); return fail_cuda(err, "cudaMemcpyAsync(H2D slab)"); }
+        e->st_h2d += n;
+        s->staged.emplace_back(slab, n);
+        s->dma_issued += n;
+        mark_dirty(e, sp, nullptr);       // the slab stays out of the ring until its job has run
+        return DM_OK;
+    }
+    int rc = dma_range(e, sp, slab, s->dma_issued, n);
+    if (rc != DM_OK) return rc;
+    s->dma_issued += n;
+    absorb_islands(s);
+    mark_dirty(e, sp, slab);
+    if (s->followers) s->cv.notify_all();
+    return DM_OK;
+}
+
+// DMA one range part.  Stream mutex held; invalidates indices into s->parts.
+int submit_part(dm_engine *e, const std::shared_ptr<Stream> &sp, size_t idx)
+{
+    Stream *s = sp.get();
+    Stream::Part pt = s->parts[idx];
+    s->parts.erase(s->parts.begin() + (long)idx);
+    if (pt.fill == 0) { slab_put(e, pt.slab); return DM_OK; }
+    e->st_ingested.fetch_add(pt.fill, std::memory_order_relaxed);
+    int rc = dma_range(e, sp, pt.slab, pt.base, pt.fill);
+    if (rc != DM_OK) return rc;
+    if (pt.base + pt.fill <= s->resume_base) add_interval(s->prefix_cover, pt.base, pt.base + pt.fill);
+    else add_interval(s->islands, pt.base, pt.base + pt.fill);
+    absorb_islands(s);
+    mark_dirty(e, sp, pt.slab);
+    if (s->followers) s->cv.notify_all();
+    return DM_OK;
+}
+
+// Would [off, off+len) collide with bytes this stream already holds?  Stream mutex held.
+bool range_taken(const Stream *s, uint64_t off, uint64_t len, const Stream::Part *self)
+{
+    const uint64_t end = off + len;
+    auto hits = [&](uint64_t lo, uint64_t hi) { return lo < end && off < hi; };
+    if (hits(s->resume_base, s->dma_issued + s->cur_fill) && !(self == nullptr && off == s->dma_issued + s->cur_fill)) return true;
+    auto in_map = [&](const std::map<uint64_t, uint64_t> &m) {
+        auto it = m.upper_bound(off);
+        if (it != m.begin() && std::prev(it)->second > off) return true;
+        return it != m.end() && it->first < end;
+    };
+    if (in_map(s->islands) || in_map(s->prefix_cover)) return true;
+    for (const Stream::Part &p : s->parts)
+        if (&p != self && hits(p.base, p.base + p.fill)) return true;
+    return false;
+}
+
+// ---- CAS commit --------------------------------------------------------------
+
+std::string json_quote(const std::string &v)
+{
+    std::string o = "\"";
+    for (unsigned char c : v) {
+        if (c == '"' || c == '\\') { o += '\\'; o += (char)c; }
+        else if (c < 0x20) { char t[8]; snprintf(t, sizeof t, "\\u%04x", c); o += t; }
+        else o += (char)c;
+    }
+    return o + "\"";
+}
+
+// The sidecar: what a hit needs besides the bytes.  The digest is over the
+// identity-encoded body, which is what HF LFS oids and OCI layer digests are defined on.
+std::string sidecar_json(const Blob &b)
+{
+    std::string o = "{\"digest\":\"sha256:" + hex_of(b.digest.b, 32) + "\",\"size\":" + std::to_string(b.size) +
+                    ",\"encoding\":\"identity\",\"engine\":\"demodel_b200\",\"abi\":" + std::to_string(DM_ABI_VERSION) +
+                    ",\"headers\":{";
+    for (size_t i = 0; i < b.meta.size(); ++i)
+        o += (i ? "," : "") + json_quote(b.meta[i].first) + ":" + json_quote(b.meta[i].second);
+    return o + "}}\n";
+}
+
+void write_sidecar(const std::string &path, const Blob &b)
+{
+    FILE *f = fopen(path.c_str(), "w");
+    if (!f) return;
+    const std::string j = sidecar_json(b);
+    fwrite(j.data(), 1, j.size(), f);
+    fclose(f);
+}
+
+std::string blob_path(const dm_engine *e, const uint8_t d[32])
+{
+    const std::string hx = hex_of(d, 32);
+    return e->cas_dir + "/blobs/sha256/" + hx.substr(0, 2) + "/" + hx;
+}
+
+// Publish a verified blob.  Returns the blob that now owns the digest (an
+// earlier copy wins; the new extents are then released).
+std::shared_ptr<Blob> publish(dm_engine *e, const Digest &d, uint64_t size, std::vector<Extent> &ext,
+                              std::vector<std::pair<std::string, std::string>> *meta)
+{
+    // trim the last extent to the bytes actually held
+    uint64_t keep = round_up(std::max<uint64_t>(size, 1), kAlign), base = 0;
+    std::vector<Extent> kept;
+    {
+        std::lock_guard<std::mutex> g(e->arena_mu);
+        for (Extent &x : ext) {
+            if (base >= keep) { e->arena.release(x.off, x.len); }
+            else if (base + x.len > keep) {
+                const uint64_t k = keep - base;
+                e->arena.release(x.off + k, x.len - k);
+                kept.push_back({x.off, k});
+            } else kept.push_back(x);
+            base += x.len;
+        }
+    }
+    ext.clear();
+    std::shared_ptr<Blob> b;
+    bool fresh = false;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        auto it = e->blobs.find(d);
+        if (it != e->blobs.end() && it->second->in_hbm) {
+            b = it->second;
+            b->tick = ++e->tick;
+        } else if (it != e->blobs.end()) {   // known on disk only: re-home into HBM
+            b = it->second;
+            b->extents = kept; kept.clear();
+            b->in_hbm = true; b->tick = ++e->tick;
+        } else {
+            b = std::make_shared<Blob>();
+            b->digest = d; b->size = size; b->extents = kept; kept.clear();
+            b->in_hbm = true; b->tick = ++e->tick;
+            if (meta) b->meta.swap(*meta);
+            e->blobs[d] = b;
+            fresh = true;
+        }
+    }
+    if (!kept.empty()) free_extents(e, kept);
+    e->st_committed++;
+    if (fresh && !e->cas_dir.empty()) {
+        {
+            std::lock_guard<std::mutex> g(e->spill_mu);
+            e->spill_q.push_back(b);
+        }
+        e->spill_cv.notify_all();
+    }
+    return b;
+}
+
+// Batch form of publish() for dm_ingest_device: every blob has exactly one right-sized extent, so
+// the index is updated under ONE lock and the arena under one more (150 k blobs per call otherwise
+// spend longer in lock traffic than in the kernel).
+void publish_many(dm_engine *e, const std::vector<Verified> &items)
+{
+    std::vector<Extent> to_free;
+    std::vector<std::shared_ptr<Blob>> to_spill;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        for (const Verified &v : items) {
+            auto it = e->blobs.find(v.d);
+            if (it != e->blobs.end() && it->second->in_hbm) {          // an earlier copy wins
+                it->second->tick = ++e->tick;
+                to_free.push_back(v.x);
+            } else if (it != e->blobs.end()) {                         // on disk only: re-home
+                Blob *b = it->second.get();
+                b->extents.assign(1, v.x);
+                b->in_hbm = true; b->tick = ++e->tick;
+            } else {
+                auto b = std::make_shared<Blob>();
+                b->digest = v.d; b->size = v.size; b->extents.assign(1, v.x);
+                b->in_hbm = true; b->tick = ++e->tick;
+                e->blobs.emplace(v.d, b);
+                if (!e->cas_dir.empty()) to_spill.push_back(b);
+            }
+        }
+    }
+    e->st_committed += items.size();
+    if (!to_free.empty()) {
+        std::lock_guard<std::mutex> g(e->arena_mu);
+        for (const Extent &x : to_free) e->arena.release(x.off, x.len);
+    }
+    if (!to_spill.empty()) {
+        {
+            std::lock_guard<std::mutex> g(e->spill_mu);
+            for (auto &b : to_spill) e->spill_q.push_back(b);
+        }
+        e->spill_cv.notify_all();
+    }
+}
+
+// Batch eviction (DM_ING_REPLACE): drop the HBM copies of these digests under one lock each way.
+void evict_many(dm_engine *e, const uint8_t *digests, uint32_t n)
+{
+    std::vector<Extent> ext;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        for (uint32_t i = 0; i < n; ++i) {
+            Digest d;
+            memcpy(d.b, digests + 32ull * i, 32);
+            auto it = e->blobs.find(d);
+            if (it == e->blobs.end() || !it->second->in_hbm || it->second->readers) continue;
+            it->second->in_hbm = false;
+            ext.insert(ext.end(), it->second->extents.begin(), it->second->extents.end());
+            it->second->extents.clear();            // under the lock (see evict_for)
+            if (!it->second->on_disk) e->blobs.erase(it);
+        }
+    }
+    free_extents(e, ext);
+}
+
+// ---- pump ----------------------------------------------------------------------
+
+// Before a stream's extents are freed or change owner: let followers' in-flight copy-outs finish.
+void wait_follow_reads(Stream *s, std::unique_lock<std::mutex> &g)
+{
+    s->cv.wait(g, [&] { return s->follow_reads == 0; });
+}
+
+void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint32_t *words)
+{
+    Stream *s = sp.get();
+    std::unique_lock<std::mutex> g(s->mu);
+    if (s->st == St::Aborted) return;
+    words_to_digest(words, s->digest.b);
+    s->matched = (!s->has_expect || s->digest == s->expect) ? 1 : 0;
+    if (s->cuda_failed) { s->matched = 0; memset(s->digest.b, 0, 32); }     // never publish under a digest the device may not have produced
+    s->completing = true;                       // no new follower copy-out starts past this point
+    wait_follow_reads(s, g);
+    std::vector<Extent> ext;
+    ext.swap(s->extents);
+    s->capacity = 0;
+    const uint64_t size = s->dma_issued;
+    const Digest d = s->digest;
+    const int matched = s->matched;
+    // a resumed stream is cacheable only if the already-hashed prefix was re-supplied
+    const bool whole = s->resume_base == 0 ||
+                       (s->prefix_cover.size() == 1 && s->prefix_cover.begin()->first == 0 &&
+                        s->prefix_cover.begin()->second >= s->resume_base);
+    g.unlock();
+    std::shared_ptr<Blob> b;
+    std::vector<std::pair<std::string, std::string>> meta;
+    g.lock(); meta.swap(s->meta); g.unlock();
+    if (matched && whole && !s->verify_only) b = publish(e, d, size, ext, &meta);
+    else { free_extents(e, ext); if (!matched) e->st_mismatch++; }
+    g.lock();
+    s->blob = b;
+    s->st = St::Done;
+    g.unlock();
+    s->cv.notify_all();
+}
+
+void reap_cycle(dm_engine *e, Cycle &c)
+{
+    float ms = 0.f;
+    if (c.njobs) {
+        cudaEventElapsedTime(&ms, c.k_start, c.k_end);
+        std::lock_guard<std::mutex> g(e->stat_mu);
+        e->st_kernel_ms += ms;
+    }
+    e->st_hashed += c.bytes;
+    for (Slab *sl : c.job_slabs) if (sl) slab_put(e, sl);
+    c.job_slabs.clear();
+    for (size_t i = 0; i < c.streams.size(); ++i) {
+        std::shared_ptr<Stream> &sp = c.streams[i];
+        bool free_now = false, wake = false;
+        {
+            std::lock_guard<std::mutex> g(sp->mu);
+            if (c.err != cudaSuccess) sp->cuda_failed = true;
+            sp->jobs_inflight--;
+            free_now = sp->st == St::Aborted && sp->jobs_inflight == 0;
+            wake = sp->ckpt_waiter;
+        }
+        if (wake) sp->cv.notify_all();
+        if (free_now) {
+            // slabs written after this job was built may still be landing in the extent (see dm_stream_abort)
+            cudaStreamSynchronize(e->copy_stream[sp->id % kCopyStreams]);
+            { std::unique_lock<std::mutex> g(sp->mu); wait_follow_reads(sp.get(), g); }
+            free_extents(e, sp->extents);
+            std::lock_guard<std::mutex> g(e->mu);
+            e->free_slots.push_back(sp->slot);
+        } else if (c.is_final[i]) {
+            complete_stream(e, sp, e->h_digests + 8ull * sp->slot);
+        }
+    }
+    c.streams.clear(); c.is_final.clear();
+    c.njobs = 0; c.bytes = 0; c.busy = false; c.err = cudaSuccess;
+}
+
+// Build one job per eligible ready stream and launch ONE multi-buffer kernel
+// over them on this cycle's CUDA stream.  Streams that still have unhashed
+// bytes afterwards (or a job in flight) stay in `ready`.
+bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &ready)
+{
+    c.njobs = 0; c.bytes = 0;
+    // One slab per job: a launch lasts as long as its longest lane, so lanes are kept the same
+    // length (streams holding more simply go again in the next launch, which overlaps this one).
+    const uint64_t quantum = (uint64_t)e->cfg.slab_bytes;
+    std::vector<std::shared_ptr<Stream>> again;
+    for (auto &sp : ready) {
+        Stream *s = sp.get();
+        std::lock_guard<std::mutex> g(s->mu);
+        if (s->st == St::Aborted || s->st == St::Done || s->final_issued) { s->queued = false; continue; }
+        // one job per stream in flight: its next job chains on the state this one writes
+        if (s->jobs_inflight || c.njobs >= e->max_jobs) { again.push_back(sp); continue; }
+        const bool finishing = s->st == St::Finishing;
+        uint64_t n = finishing ? (s->dma_issued - s->hash_issued) : ((s->dma_issued - s->hash_issued) & ~63ull);
+        if (!finishing && n == 0) { s->queued = false; continue; }
+        uint64_t contig = 0;
+        uint8_t *src = nullptr;
+        bool final = finishing;
+        Slab *job_slab = nullptr;
+        if (s->verify_only) {
+            if (!s->staged.empty()) {
+                job_slab = s->staged.front().first;
+                n = s->staged.front().second;               // whole slab; only the last may hold a partial block
+                src = job_slab->dev;
+                s->staged.pop_front();
+                final = finishing && s->staged.empty();
+                if (!final && (n & 63)) { final = false; }   // cannot happen: mid-stream slabs are full
+            } else if (!finishing) { s->queued = false; continue; }
+            else n = 0;
+        } else {
+            src = n ? seg_at(e, s->extents, s->hash_issued, &contig) : nullptr;
+            if (n > contig && n) { n = contig; final = false; }          // stop at the extent boundary
+            if (n > quantum) { n = quantum; final = false; }
+        }
+        dm::HashJob &jb = c.h_jobs[c.njobs++];
+        jb.src = src; jb.dst = nullptr; jb.nbytes = n; jb.total_len = s->dma_issued; jb.slot = s->slot;
+        jb.flags = (s->hash_issued == 0 ? dm::JOB_INIT : 0u) | (final ? dm::JOB_FINAL : 0u);
+        jb.one = 1; jb.pad_ = 0;
+        s->hash_issued += n;
+        s->jobs_inflight++;
+        if (final) s->final_issued = true;
+        c.bytes += n;
+        c.streams.push_back(sp);
+        c.is_final.push_back(final ? 1 : 0);
+        c.job_slabs.push_back(job_slab);
+        if (!final && (finishing || !s->staged.empty() || (!s->verify_only && ((s->dma_issued - s->hash_issued) & ~63ull)))) again.push_back(sp);
+        else s->queued = false;
+    }
+    ready.swap(again);
+    if (c.njobs == 0) return false;
+
+    // Everything whose DMA was enqueued before this point is covered by these events.
+    for (int i = 0; i < kCopyStreams; ++i) {
+        cudaEventRecord(c.copy_ev[i], e->copy_stream[i]);
+        cudaStreamWaitEvent(c.stream, c.copy_ev[i], 0);
+    }
+    // Launches overlap on the GPU, so what decides the kernel shape is how many jobs will be
+    // co-resident (this launch + those still running), not the size of this launch alone.
+    uint32_t resident = c.njobs;
+    for (const Cycle &o : e->cycles) if (o.busy) resident += o.njobs;
+    const int spw = e->force_spw ? e->force_spw : dm::streams_per_warp_for(resident);
+    c.deep = spw == 1;
+    if (spw > 1) {
+        // lanes of a warp run in lock step: keep neighbours the same length
+        std::vector<uint32_t> order(c.njobs);
+        for (uint32_t i = 0; i < c.njobs; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](uint32_t a, uint32_t b) { return c.h_jobs[a].nbytes > c.h_jobs[b].nbytes; });
+        std::vector<dm::HashJob> tmp(c.h_jobs, c.h_jobs + c.njobs);
+        std::vector<std::shared_ptr<Stream>> st2(c.njobs);
+        std::vector<uint8_t> fin2(c.njobs);
+        std::vector<Slab *> sl2(c.njobs);
+        for (uint32_t i = 0; i < c.njobs; ++i) { c.h_jobs[i] = tmp[order[i]]; st2[i] = c.streams[order[i]]; fin2[i] = c.is_final[order[i]]; sl2[i] = c.job_slabs[order[i]]; }
+        c.streams.swap(st2); c.is_final.swap(fin2); c.job_slabs.swap(sl2);
+    }
+    // A failure anywhere here (or reported later by the end event) marks every stream of the launch:
+    // their verdict becomes "not matched" and nothing is published (reap_cycle / complete_stream).
+    (void)cudaGetLastError();           // nothing stale may be mistaken for this launch's result
+    auto note = [&](cudaError_t r) { if (r != cudaSuccess && r != cudaErrorNotReady && c.err == cudaSuccess) c.err = r; };
+    note(cudaMemcpyAsync(c.d_jobs, c.h_jobs, sizeof(dm::HashJob) * c.njobs, cudaMemcpyHostToDevice, c.stream));
+    note(cudaEventRecord(c.k_start, c.stream));
+    if (c.err != cudaSuccess) { /* the job table may not be on the device: launching would run stale jobs */ }
+    else if (spw == 1) { note(dm::launch_sha256_deep(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_deep)); e->st_deep++; }
+    else if (spw == 32) { note(dm::launch_sha256_wide(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, e->variant_wide)); e->st_wide++; }
+    else { note(dm::launch_sha256_group(c.d_jobs, c.njobs, e->d_states, e->d_digests, c.stream, spw, e->variant_deep)); e->st_group++; }
+    e->st_launches++;
+    note(cudaEventRecord(c.k_end, c.stream));
+    c.busy = true;
+    return true;
+}
+
+// Ring back-pressure relief (pump thread): DMA the partly filled slabs of open streams - the sequential
+// one and those of range parts (a client fetching one blob as P parallel ranges holds P of them) - so
+// they return to the ring.  try_lock only: a stream busy in a write keeps its slabs this round.
+void flush_partial_slabs(dm_engine *e)
+{
+    std::vector<std::shared_ptr<Stream>> all;
+    for (int k = 0; k < kStripes; ++k) {
+        std::lock_guard<std::mutex> g(e->stripe_mu[k]);
+        for (auto &kv : e->streams[k]) all.push_back(kv.second);
+    }
+    for (auto &sp : all) {
+        Stream *s = sp.get();
+        std::unique_lock<std::mutex> g(s->mu, std::try_to_lock);
+        if (!g.owns_lock() || s->st != St::Open || s->window_out) continue;
+        // a part that was sent early simply becomes an island; the range continues in a fresh part
+        for (size_t i = s->parts.size(); i-- > 0;)
+            if (s->parts[i].fill) submit_part(e, sp, i);
+        if (!s->cur || s->cur_fill == 0) continue;
+        if (s->verify_only && (s->cur_fill & 63)) {              // slab-by-slab hashing needs whole blocks:
+            const uint32_t whole = s->cur_fill & ~63u;           // send those, keep the tail in the stream
+            s->carry_fill = s->cur_fill - whole;
+            memcpy(s->carry, s->cur->host + whole, s->carry_fill);
+            s->cur_fill = whole;                                 // (0 whole blocks: submit_slab just returns the slab)
+        }
+        submit_slab(e, sp);
+    }
+}
+
+// The pump owns all launch decisions.  Policy: at most one JOB PER STREAM in
+// flight (its next job chains on the state the running one writes), but up to
+// kCycles LAUNCHES in flight, each on its own CUDA stream.  A launch costs its
+// longest lane however few lanes it has, so a launch that caught only a few
+// early streams must not hold the others back: they go out in the next launch
+// and overlap with it on the GPU (a deep launch occupies one sub-partition per
+// job).  When every launch slot is busy the ready set simply accumulates.
+void pump_main(dm_engine *e)
+{
+    cudaSetDevice(e->device);
+    int n_inflight = 0;
+    int b_head = 0, b_tail = 0, b_live = 0;
+    std::vector<std::shared_ptr<Stream>> ready, inbox;
+    std::vector<Slab *> slabs;
+    int starve_ticks = 0;
+    bool retry_ready = false;       // ready streams blocked only by their own in-flight job
+    bool launched = false;
+    for (;;) {
+        // 1. ring slabs whose DMA has completed go back to the writers
+        while (b_live) {
+            SlabBatch &b = e->batches[b_tail];
+            bool done = true;
+            for (int i = 0; i < kCopyStreams; ++i) done = done && poll_event(b.ev[i]) == cudaSuccess;
+            if (!done) break;
+            for (Slab *sl : b.slabs) slab_put(e, sl);
+            b.slabs.clear(); b.busy = false;
+            b_tail = (b_tail + 1) % kSlabBatches; --b_live;
+        }
+        // a recall can miss slabs (stream busy in a write, window lent out): repeat while writers wait
+        if (e->ring_starved.exchange(false) || (e->ring_waiters.load() > 0 && ++starve_ticks >= 16)) {
+            starve_ticks = 0;
+            flush_partial_slabs(e);
+        }
+        // 2. finished hash launches (any order)
+        bool reaped = false;
+        for (Cycle &c : e->cycles)
+            if (c.busy) {
+                const cudaError_t q = poll_event(c.k_end);
+                if (q == cudaErrorNotReady) continue;
+                if (q != cudaSuccess && c.err == cudaSuccess) c.err = q;       // a faulted launch must end, not hang its streams
+                reap_cycle(e, c); --n_inflight; reaped = true;
+            }
+        // 3. inbox.  Sleep unless the previous pass launched something (more may be launchable).
+        bool stopping;
+        {
+            std::unique_lock<std::mutex> g(e->work_mu);
+            const bool idle = !n_inflight && !b_live && ready.empty() && slabs.empty();
+            if (e->dirty.empty() && e->pending_slabs.empty() && !e->stop && !launched && !reaped) {
+                if (idle && e->ring_waiters.load() == 0)
+                    e->work_cv.wait(g, [&] { return !e->dirty.empty() || !e->pending_slabs.empty() || e->stop || e->ring_starved.load(); });
+                else e->work_cv.wait_for(g, std::chrono::microseconds(40));
+            }
+            stopping = e->stop;
+            inbox.swap(e->dirty);
+            if (slabs.empty()) slabs.swap(e->pending_slabs);
+            else { slabs.insert(slabs.end(), e->pending_slabs.begin(), e->pending_slabs.end()); e->pending_slabs.clear(); }
+        }
+        launched = false;
+        const bool fresh = !inbox.empty();
+        for (auto &sp : inbox) ready.push_back(sp);
+        inbox.clear();
+        // 4. tag the newly DMA'd slabs with copy events
+        if (!slabs.empty() && b_live < kSlabBatches) {
+            SlabBatch &b = e->batches[b_head];
+            b.slabs.swap(slabs);
+            for (int i = 0; i < kCopyStreams; ++i) cudaEventRecord(b.ev[i], e->copy_stream[i]);
+            b.busy = true;
+            b_head = (b_head + 1) % kSlabBatches; ++b_live;
+        }
+        // 5. launch on a free slot.  With launches already running, let the ready set
+        //    build up to a worthwhile size first (they will all fit in one launch anyway).
+        if (!ready.empty() && n_inflight < kCycles && (fresh || reaped || !retry_ready)) {
+            const uint64_t open_now = e->n_streams;
+            const bool worthwhile = n_inflight == 0 || ready.size() * 8 >= open_now || ready.size() >= 4096;
+            if (worthwhile) {
+                for (Cycle &c : e->cycles) {
+                    if (c.busy) continue;
+                    const size_t before = ready.size();
+                    if (run_cycle(e, c, ready)) { ++n_inflight; retry_ready = false; launched = true; }
+                    else retry_ready = !ready.empty() && ready.size() == before;   // all blocked on their own jobs
+                    break;
+                }
+            }
+        }
+        if (stopping && !n_inflight && !b_live && ready.empty() && slabs.empty()) {
+            std::lock_guard<std::mutex> g(e->work_mu);
+            if (e->dirty.empty() && e->pending_slabs.empty()) break;
+        }
+    }
+}
+
+// ---- disk tier -----------------------------------------------------------------
+
+Bounce *bounce_get(dm_engine *e)
+{
+    std::unique_lock<std::mutex> g(e->bounce_mu);
+    e->bounce_cv.wait(g, [&] { return !e->bounce_free.empty(); });
+    Bounce *b = e->bounce_free.back();
+    e->bounce_free.pop_back();
+    return b;
+}
+Bounce *bounce_try_get(dm_engine *e)      // for long-lived borrowers: leaves a reserve
+{
+    std::lock_guard<std::mutex> g(e->bounce_mu);
+    if ((int)e->bounce_free.size() <= kBounceReserve) return nullptr;
+    Bounce *b = e->bounce_free.back();
+    e->bounce_free.pop_back();
+    return b;
+}
+void bounce_put(dm_engine *e, Bounce *b)
+{
+    { std::lock_guard<std::mutex> g(e->bounce_mu); e->bounce_free.push_back(b); }
+    e->bounce_cv.notify_one();
+}
+
+void mkdirs(const std::string &path)
+{
+    for (size_t i = 1; i < path.size(); ++i)
+        if (path[i] == '/') { std::string p = path.substr(0, i); mkdir(p.c_str(), 0755); }
+}
+
+bool spill_one(dm_engine *e, Blob *b)
+{
+    const std::string path = blob_path(e, b->digest.b), tmp = path + ".part";
+    mkdirs(path);
+    int fd = open(tmp.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+    if (fd < 0) return false;
+    // two pinned buffers: the D2H of piece k+1 runs while piece k is written to the file
+    Bounce *bn[2] = {bounce_get(e), bounce_get(e)};
+    uint64_t piece_len[2] = {0, 0};
+    bool ok = true;
+    auto start_piece = [&](int slot, uint64_t off) {
+        const uint64_t n = std::min<uint64_t>(kBounceBytes, b->size - off);
+        uint8_t *dst = bn[slot]->host;
+        cudaError_t err = cudaSuccess;
+        for_segments(e, b->extents, off, n, [&](uint8_t *dev, uint64_t len) {
+            if (err == cudaSuccess) err = cudaMemcpyAsync(dst, dev, len, cudaMemcpyDeviceToHost, bn[slot]->stream);
+            dst += len;
+        });
+        piece_len[slot] = n;
+        return err == cudaSuccess;
+    };
+    uint64_t issued = 0, written = 0;
+    int cur = 0;
+    if (b->size) { ok = start_piece(0, 0); issued = piece_len[0]; }
+    while (ok && written < b->size) {
+        if (issued < b->size) { ok = start_piece(cur ^ 1, issued); issued += piece_len[cur ^ 1]; }
+        if (cudaStreamSynchronize(bn[cur]->stream) != cudaSuccess) { ok = false; break; }
+        const uint64_t n = piece_len[cur];
+        e->st_d2h += n;
+        uint64_t w = 0;
+        while (w < n) {
+            ssize_t r = write(fd, bn[cur]->host + w, n - w);
+            if (r < 0) { if (errno == EINTR) continue; ok = false; break; }
+            w += (uint64_t)r;
+        }
+        written += n;
+        cur ^= 1;
+    }
+    cudaStreamSynchronize(bn[0]->stream);
+    cudaStreamSynchronize(bn[1]->stream);
+    bounce_put(e, bn[0]);
+    bounce_put(e, bn[1]);
+    close(fd);
+    if (ok) ok = rename(tmp.c_str(), path.c_str()) == 0;
+    if (ok) write_sidecar(path + ".meta", *b);
+    else unlink(tmp.c_str());
+    return ok;
+}
+
+void spill_main(dm_engine *e)
+{
+    cudaSetDevice(e->device);
+    for (;;) {
+        std::shared_ptr<Blob> b;
+        {
+            std::unique_lock<std::mutex> g(e->spill_mu);
+            e->spill_cv.wait(g, [&] { return !e->spill_q.empty() || e->stop; });
+            if (e->spill_q.empty()) break;
+            b = e->spill_q.front();
+            e->spill_q.pop_front();
+        }
+        bool have;
+        {
+            std::lock_guard<std::mutex> g(e->mu);
+            have = b->in_hbm;
+            if (have) b->readers++;        // pin against eviction while copying out
+        }
+        bool ok = have && spill_one(e, b.get());
+        {
+            std::lock_guard<std::mutex> g(e->mu);
+            if (have) b->readers--;
+            b->on_disk = ok;
+            b->spill_done = true;
+        }
+        {
+            std::lock_guard<std::mutex> g(e->spill_mu);
+        }
+        e->spill_done_cv.notify_all();
+    }
+}
+
+// The device mirror of the ring exists from the start with DM_F_NO_HBM_CAS, otherwise it is
+// allocated the first time a blob too large for the arena shows up.
+int ensure_dev_ring(dm_engine *e)
+{
+    std::lock_guard<std::mutex> g(e->slab_mu);
+    if (e->dev_ring) return DM_OK;
+    cudaSetDevice(e->device);
+    const uint64_t bytes = (uint64_t)e->slab_store.size() * e->cfg.slab_bytes;
+    CU_TRY(cudaMalloc(&e->dev_ring, bytes));
+    for (size_t i = 0; i < e->slab_store.size(); ++i) e->slab_store[i].dev = e->dev_ring + i * e->cfg.slab_bytes;
+    return DM_OK;
+}
+
+std::shared_ptr<Stream> find_stream(dm_engine *e, uint64_t id)
+{
+    const int k = (int)(id % kStripes);
+    std::lock_guard<std::mutex> g(e->stripe_mu[k]);
+    auto it = e->streams[k].find(id);
+    return it == e->streams[k].end() ? nullptr : it->second;
+}
+
+void drop_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, bool release_slot)
+{
+    const int k = (int)(sp->id % kStripes);
+    {
+        std::lock_guard<std::mutex> g(e->stripe_mu[k]);
+        if (e->streams[k].erase(sp->id)) e->n_streams--;
+    }
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        if (release_slot) e->free_slots.push_back(sp->slot);
+        if (sp->has_expect) {
+            auto it = e->inflight.find(sp->expect);
+            if (it != e->inflight.end() && (it->second.expired() || it->second.lock() == sp)) e->inflight.erase(it);
+        }
+    }
+}
+
+int ensure_ingest_scratch(dm_engine *e, uint32_t n)
+{
+    if (n <= e->ing_cap) return DM_OK;
+    const uint32_t cap = std::max<uint32_t>(n, 4096);
+    if (e->ing_states) { cudaFree(e->ing_states); cudaFree(e->ing_digests); cudaFree(e->ing_jobs_d);
+                         cudaFreeHost(e->ing_jobs_h); cudaFreeHost(e->ing_digests_h); e->ing_cap = 0; }
+    CU_TRY(cudaMalloc(&e->ing_states, 32ull * cap));
+    CU_TRY(cudaMalloc(&e->ing_digests, 32ull * cap));
+    CU_TRY(cudaMalloc(&e->ing_jobs_d, sizeof(dm::HashJob) * (uint64_t)cap));
+    CU_TRY(cudaHostAlloc(&e->ing_jobs_h, sizeof(dm::HashJob) * (uint64_t)cap, cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&e->ing_digests_h, 32ull * cap, cudaHostAllocDefault));
+    e->ing_cap = cap;
+    return DM_OK;
+}
+
+}  // namespace dmi

@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY — a fake "CUDA runtime" (asynchronous: one worker thread per stream) so that the engine's host
-// logic (demodel_b200/csrc/engine.cu: ring, pump thread, CAS, ranges, followers, disk tier) can be
+// logic (demodel_b200/csrc/engine_*.cu: ring, pump thread, CAS, ranges, followers, disk tier) can be
 // compiled with plain g++ and soaked under ThreadSanitizer / ASan on a box with no GPU.
 // Device memory is host memory; copies and "kernels" run later on the stream's worker thread in FIFO order;
 // events carry record generations (query / synchronize / stream-wait behave like CUDA's); the SHA-256

@@ -42,7 +42,7 @@ def _build_rig(exe, *flags):
 
 
 def test_engine_host_logic_soak_under_tsan_and_asan(tmp_path):
-    """The whole engine (engine.cu + proxy driver + manifest) compiled with plain g++ against a fake CUDA
+    """The whole engine (engine_*.cu + proxy driver + manifest) compiled with plain g++ against a fake CUDA
     runtime that is asynchronous like the real one (a worker thread per stream; copies and 'kernels' - the
     CPU oracle - run there; tests/native/fake_cuda*: test infrastructure, never part of the product), so
     that touching a slab, extent or job table before the event guarding it is a data race TSan reports;
@@ -117,7 +117,8 @@ def test_python_mirror_gpu_test_logic_and_bench_flow_over_the_fake_runtime(tmp_p
     cs = os.path.join(ROOT, "demodel_b200", "csrc")
     build = subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread",
                             "-I", os.path.join(ROOT, "tests", "native", "fake_cuda"), "-o", str(lib), "-x", "c++",
-                            os.path.join(cs, "engine.cu"), os.path.join(cs, "proxy_driver.cc"), os.path.join(cs, "manifest.cc"),
+                            os.path.join(cs, "engine_core.cu"), os.path.join(cs, "engine_api.cu"), os.path.join(cs, "engine_cache.cu"),
+                            os.path.join(cs, "proxy_driver.cc"), os.path.join(cs, "manifest.cc"),
                             os.path.join(ROOT, "tests", "native", "fake_cuda.cc")], capture_output=True, text=True, timeout=600)
     assert build.returncode == 0, build.stderr[-3000:]
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "native", "run_mirror_tests.py"), str(lib)],
