@@ -49,6 +49,16 @@ WORKLOADS = {
     # 148 SMs x 4 sub-partitions x 8 warps x 32 lanes = 151552 streams
     "saturate_151552x112KiB": {"sizes": [112 << 10] * 151552, "baseline_config": None},
     "tiny": {"sizes": [1 << 20] * 64, "baseline_config": None},
+    # BASELINE.json configs[3]: Ollama manifest + 7B GGUF layer blobs (SURVEY.md section 8d sizes: model layer of a
+    # typical 7B Q4_0, license, params, config), digest verify sharded by dm_shard_of over the ranks
+    # (4 B200 in the config).  One layer dominates: one chain on one GPU, whatever N is.
+    "ollama_7b_manifest": {"sizes": [3826793677, 11357, 17, 420], "baseline_config": 3, "routing": "digest"},
+    # BASELINE.json configs[4]: blob-size sweep, scaled DOWN and saying so: classes 1 MiB .. 1 GiB in x4 steps
+    # (the config's 64 GiB top class is one 14-minute serial chain on any number of GPUs), 2 GiB per class per
+    # GPU = 12 GiB per GPU per step (the config: 1 TB over 8 GPUs = 125 GB per GPU) - per-class GB/s in `classes`.
+    "size_sweep": {"sizes": [sz for k in range(20, 31, 2) for sz in [1 << k] * ((2 << 30) >> k)], "baseline_config": 4,
+                   "classes": [1 << k for k in range(20, 31, 2)],
+                   "scaled": "top class 1 GiB instead of 64 GiB (x1/64), 12 GiB per GPU per step instead of 125 GB (x1/10)"},
 }
 
 
@@ -142,6 +152,40 @@ def _my_blob_indices(n_blobs, rank, world):
             out.append(k)
         k += 1
     return out
+
+
+def _digest_routed_set(eng, torch, dist, n_total, size_of, rank, world, local, base=0):
+    """Fixed blob set routed the production way: the digests of blobs 0..n_total-1 are learned once (each rank
+    hashes a 1/world slice, hash-only; the digests are exchanged - setup, outside any timed region), then every rank
+    keeps the blobs dm_shard_of(digest, world) gives it.  Returns (indices owned, digests of all, per-rank counts)."""
+    import numpy as np
+    from demodel_b200.engine import shard_of
+    mine_slice = list(range(rank, n_total, world))
+    sizes = [size_of(i) for i in mine_slice]
+    offs, span = _layout(sizes)
+    digs_local = np.zeros((len(mine_slice), 32), dtype=np.uint8)
+    if mine_slice:
+        buf = torch.empty(max(span, 16), dtype=torch.uint8, device=f"cuda:{local}")
+        for j, i in enumerate(mine_slice):
+            eng.synth_fill_device(SEED, base + i, 0, buf.data_ptr() + offs[j], sizes[j])
+        d, _, _ = eng.ingest_device(buf.data_ptr(), offs, sizes, hash_only=True, raw=True)
+        digs_local = d.reshape(-1, 32).copy()
+        del buf
+    all_digs = np.zeros((n_total, 32), dtype=np.uint8)
+    if world > 1:
+        per = (n_total + world - 1) // world
+        send = torch.zeros((per, 32), dtype=torch.uint8, device=f"cuda:{local}")
+        send[:len(mine_slice)] = torch.from_numpy(digs_local).to(send.device)
+        got = [torch.zeros_like(send) for _ in range(world)]
+        dist.all_gather(got, send)
+        for r in range(world):
+            idx = list(range(r, n_total, world))
+            all_digs[idx] = got[r][:len(idx)].cpu().numpy()
+    else:
+        all_digs[mine_slice] = digs_local
+    owner = [shard_of(all_digs[i].tobytes(), world) for i in range(n_total)]
+    counts = [owner.count(r) for r in range(world)]
+    return [i for i in range(n_total) if owner[i] == rank], all_digs, counts
 
 
 class ClockSampler:
@@ -304,21 +348,34 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sizes = WORKLOADS[args.workload]["sizes"]
+    wl = WORKLOADS[args.workload]
+    routing = wl.get("routing", "url")
+    hbm_peak, peak_src = _peaks()
+    sizes_all = wl["sizes"]
+    if routing == "digest":
+        # FIXED blob set (strong scaling): blob i goes to the rank dm_shard_of(digest_i, world) names; a rank may own
+        # nothing.  The digests are learned first (setup), as a manifest would have announced them.
+        boot = demodel_b200.Engine(device=local, hbm_cas_bytes=256 << 20, ring_bytes=64 << 20)
+        mine, all_digs, shard_counts = _digest_routed_set(boot, torch, dist, len(sizes_all), lambda i: sizes_all[i], rank, world, local)
+        boot.close()
+        sizes = [sizes_all[i] for i in mine]
+    else:
+        sizes = sizes_all
+        mine = _my_blob_indices(len(sizes), rank, world)
+        shard_counts = None
     n = len(sizes)
     offs, span = _layout(sizes)
     offs_arr = np.asarray(offs, dtype=np.uint64)      # converted once: no per-step list marshalling
     sizes_arr = np.asarray(sizes, dtype=np.uint64)
     total = sum(sizes)
-    mine = _my_blob_indices(n, rank, world)
-    hbm_peak, peak_src = _peaks()
+    job_total = sum(sizes_all) if routing == "digest" else total * world      # bytes the whole job moves per step
 
-    cas_bytes = 0 if args.hash_only else span + (64 << 20)
-    eng = demodel_b200.Engine(device=local, hbm_cas_bytes=max(cas_bytes, 256 << 20) + (4 << 30), ring_bytes=args.ring_mib << 20,
+    cas_bytes = 0 if args.hash_only else (span + (64 << 20) if world == 1 else int(1.5 * span) + (64 << 20))   # N > 1: room for the
+    eng = demodel_b200.Engine(                                                                          # digest-routed probe's uneven sharesdevice=local, hbm_cas_bytes=max(cas_bytes, 256 << 20) + (4 << 30), ring_bytes=args.ring_mib << 20,
                               slab_bytes=args.slab_kib << 10, max_streams=max(65536, n + 1024))
-    dev = torch.empty(span, dtype=torch.uint8, device=f"cuda:{local}")
+    dev = torch.empty(max(span, 16), dtype=torch.uint8, device=f"cuda:{local}")
     # blob indices are consecutive per rank only when world == 1; fill one by one otherwise
-    if mine == list(range(mine[0], mine[0] + n)):
+    if n and mine == list(range(mine[0], mine[0] + n)):
         eng.synth_fill_device_many(SEED, mine[0], dev.data_ptr(), offs, sizes)
     else:
         for i, k in enumerate(mine):
@@ -357,19 +414,49 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     wall_max, kernel_ms_max = float(tt[0]), float(tt[1])
-    value = total * world * args.steps / wall_max / 1e9
+    value = job_total * args.steps / wall_max / 1e9
     bytes_per_blob_byte = 1 if args.hash_only else 2
-    achieved = bytes_per_blob_byte * total * args.steps / (kernel_ms_max / 1e3) / 1e9
+    # roofline of the dominant kernel on the busiest rank: its algorithmic bytes / its CUDA-event time
+    tb = torch.tensor([float(total)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    achieved = bytes_per_blob_byte * float(tb[0]) * args.steps / (max(kernel_ms_max, 1e-9) / 1e3) / 1e9
 
     # spot check against an independent implementation on the host (hashlib), outside the timed region
     import hashlib
-    probe = min(range(n), key=lambda i: sizes[i])
-    host_probe = dev[offs[probe]:offs[probe] + sizes[probe]].cpu().numpy()
-    assert hashlib.sha256(host_probe.tobytes()).digest() == digs[probe], "GPU digest differs from hashlib"
+    if n:
+        probe = min(range(n), key=lambda i: sizes[i])
+        host_probe = dev[offs[probe]:offs[probe] + sizes[probe]].cpu().numpy()
+        assert hashlib.sha256(host_probe.tobytes()).digest() == digs[probe], "GPU digest differs from hashlib"
+    if routing == "digest":                             # the routed digests are the ones the timed steps verified against
+        assert [all_digs[i].tobytes() for i in mine] == digs
+
+    # ---- size sweep: each size class on its own (kernel time; inputs and expectations as in the aggregate pass) ----
+    classes = None
+    if wl.get("classes"):
+        classes = []
+        for csz in wl["classes"]:
+            idx = [i for i in range(n) if sizes[i] == csz]
+            if not idx:
+                continue
+            lo, hi = idx[0], idx[-1] + 1
+            exp_c = expect[32 * lo:32 * hi]
+            kms = []
+            for it in range(2):                          # one untimed pass, one measured (the aggregate leg above is the warm-up proper)
+                _, mc, ms_ = eng.ingest_device(dev.data_ptr(), offs_arr[lo:hi], sizes_arr[lo:hi], expect=exp_c, replace=True, raw=True)
+                assert mc.all()
+                kms.append(ms_)
+            tc = torch.tensor([kms[-1]], dtype=torch.float64, device=f"cuda:{local}")
+            if world > 1:
+                dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            cb = csz * len(idx)
+            classes.append({"blob_bytes": csz, "blobs_per_gpu": len(idx), "bytes_per_gpu": cb, "kernel_ms": float(tc[0]),
+                            "GBps": cb * world / (float(tc[0]) / 1e3) / 1e9, "kernel": _kernel_for(len(idx)),
+                            "hbm_frac": 2 * cb / (float(tc[0]) / 1e3) / 1e9 / hbm_peak})
 
     # ---- probes: the other kernel shapes at stream counts that fill the chip (kernel time only) ----
     probes = None
-    if rank == 0 and not args.no_probes and args.blobs == 0:
+    if rank == 0 and not args.no_probes and args.blobs == 0 and routing == "url" and not wl.get("classes"):
         probes = {}
         for name, pn, pbytes in (("wide_151552_streams", 151552, 16384), ("group8_4096_streams", 4096, 524288)):
             po = np.arange(pn, dtype=np.uint64) * np.uint64(pbytes)
@@ -454,8 +541,9 @@ def main():
             eng.proxy_serve(digs[:min(n, 8)], out, hoff[:min(n, 8) + 1], chunk=1 << 20, nthreads=drive_threads)   # warm
             secs = eng.proxy_serve(digs, out, hoff, chunk=1 << 20, nthreads=drive_threads)
             probe_i = n // 2
-            assert np.array_equal(out[int(hoff[probe_i]):int(hoff[probe_i + 1])], host[int(hoff[probe_i]):int(hoff[probe_i + 1])])
-            serve = {"value": total / secs / 1e9, "unit": UNIT, "threads": drive_threads, "read_bytes": 1 << 20,
+            if n:
+                assert np.array_equal(out[int(hoff[probe_i]):int(hoff[probe_i + 1])], host[int(hoff[probe_i]):int(hoff[probe_i + 1])])
+            serve = {"value": total / max(secs, 1e-9) / 1e9, "unit": UNIT, "threads": drive_threads, "read_bytes": 1 << 20,
                      "api": "dm_proxy_serve -> dm_cache_open/read/close"}
             for d_ in digs:
                 eng.cache_evict(d_)
@@ -463,7 +551,7 @@ def main():
         te = torch.tensor([e_wall], dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": total * world * e2e_steps / float(te[0]) / 1e9, "unit": UNIT,
+        e2e = {"value": job_total * e2e_steps / float(te[0]) / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": total, "d2h_bytes_per_step": 32 * n, "steps": e2e_steps,
                "launches_per_step": (es1["kernel_launches"] - es0["kernel_launches"]) / e2e_steps,
                "kernel_ms_sum_per_step": (es1["kernel_ms"] - es0["kernel_ms"]) / e2e_steps,
@@ -472,6 +560,63 @@ def main():
                "api": "dm_proxy_drive -> dm_stream_open/write/flush/finish, 32 KiB pieces, %d concurrent bodies on %d threads%s"
                       % (conc, drive_threads, ", zero-copy ring windows" if args.e2e_zero_copy else "")}
         del host
+
+    # ---- digest-prefix sharding of a FIXED set (N > 1): what the weak-scaling line above cannot show -------------
+    # The headline gives every rank exactly n blobs.  Production routes by dm_shard_of(digest): a fixed set of
+    # n x N blobs lands unevenly (binomial).  Measured here: per-rank counts, the imbalance, and the whole-set rate
+    # with the barrier-to-barrier time of the slowest rank.
+    sharding = None
+    if world > 1 and routing == "url" and not args.no_probes and args.blobs == 0 and not wl.get("classes") and not args.hash_only:
+        for d_ in digs:
+            eng.cache_evict(d_)
+        del dev
+        torch.cuda.empty_cache()
+        n_fixed = n * world
+        owned, fd, counts = _digest_routed_set(eng, torch, dist, n_fixed, lambda i: sizes[i % n], rank, world, local, base=1 << 24)
+        fdev, ready = None, 1.0
+        try:                                  # a rank-local failure (its share does not fit) must not leave the others in a collective
+            fs = [sizes[i % n] for i in owned]
+            fo, fspan = _layout(fs)
+            fdev = torch.empty(max(fspan, 16), dtype=torch.uint8, device=f"cuda:{local}")
+            for j, i in enumerate(owned):
+                eng.synth_fill_device(SEED, (1 << 24) + i, 0, fdev.data_ptr() + fo[j], fs[j])
+            fexp = b"".join(fd[i].tobytes() for i in owned)
+            fo_a, fs_a = np.asarray(fo, dtype=np.uint64), np.asarray(fs, dtype=np.uint64)
+            for _ in range(2):
+                _, fm, _ = eng.ingest_device(fdev.data_ptr(), fo_a, fs_a, expect=fexp, replace=True, raw=True)
+                assert fm.all()
+        except Exception as ex:                # noqa: BLE001
+            ready = 0.0
+            sharding = {"error": f"rank {rank}: {ex!r}", "blobs_per_rank": counts}
+        agree = torch.tensor([ready], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if float(agree[0]) > 0:
+            f_steps = max(1, min(args.steps, 3))
+            barrier()
+            t0 = time.perf_counter()
+            fk = 0.0
+            for _ in range(f_steps):
+                _, fm, ms_ = eng.ingest_device(fdev.data_ptr(), fo_a, fs_a, expect=fexp, replace=True, raw=True)
+                fk += ms_
+            barrier()
+            f_wall = time.perf_counter() - t0
+            tf = torch.tensor([f_wall, fk, 1.0 if fm.all() else 0.0], dtype=torch.float64, device=f"cuda:{local}")
+            tmin = tf.clone()
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            fbytes = sum(sizes[i % n] for i in range(n_fixed))
+            sharding = {"mode": "fixed set routed by dm_shard_of(digest, N)", "blobs": n_fixed, "blobs_per_rank": counts,
+                        "imbalance_max_over_mean": max(counts) / (n_fixed / world), "steps": f_steps, "all_verified": bool(float(tmin[2]) > 0),
+                        "value": fbytes * f_steps / float(tf[0]) / 1e9, "unit": UNIT, "ms_per_step": 1e3 * float(tf[0]) / f_steps,
+                        "kernel_ms_per_step_max_rank": float(tf[1]) / f_steps,
+                        "note": "warp-per-stream regime: a rank's time is its longest chain, not its blob count, while it holds "
+                                "<= 592 streams (one per sub-partition) - the imbalance costs HBM, not time"}
+        elif sharding is None:
+            sharding = {"error": "another rank could not set up its share", "blobs_per_rank": counts}
+        for i in owned:
+            eng.cache_evict(fd[i].tobytes())
+        del fdev
+        dev = torch.empty(16, dtype=torch.uint8, device=f"cuda:{local}")
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) -----------------------
     cpu = None
@@ -528,18 +673,22 @@ def main():
                 traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True, "scaling": "strong" if routing == "digest" else "weak",
+            "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": args.workload, "baseline_config": WORKLOADS[args.workload]["baseline_config"],
                        "blobs_per_gpu": n, "bytes_per_gpu_per_step": total, "mode": "hash-only" if args.hash_only else "hash-and-cache (fused CAS copy)",
                        "kernel": args.kernel or _kernel_for(n), "seed": hex(SEED),
                        "l2": "inputs (%.1f GB) larger than L2 (126 MB); no flush needed" % (total / 1e9),
-                       "parallelism": f"shard{world} (URL-hash homed, no collective)"},
+                       "parallelism": (f"shard{world} (fixed set routed by dm_shard_of(digest), no collective)" if routing == "digest"
+                                       else f"shard{world} (URL-hash homed, no collective)"),
+                       "blobs_per_rank": shard_counts, "scaled": wl.get("scaled"), "job_bytes_per_step": job_total},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_blob_byte": bytes_per_blob_byte, "kernel_ms_per_step": kernel_ms_max / args.steps,
                          "int_issue": _int_issue_roofline(n, achieved / bytes_per_blob_byte, (clocks or {}).get("sm_mhz"))},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "probes": probes,
+            "classes": classes, "sharding": sharding,
             "notes": {
                 "workload_choice": "BASELINE configs[2] (256 x 64 MiB, 17.18 GB) is the largest single-GPU configuration; "
                                    "configs[1] (4 Llama-3-8B shards, 16.06 GB) is selectable with --workload llama3_8b_shards",

@@ -17,6 +17,7 @@ DM_OK, DM_EINVAL, DM_ENOMEM, DM_ENOENT, DM_ECUDA, DM_ESTATE, DM_EIO, DM_ENODEV, 
 
 DM_F_NO_HBM_CAS = 0x1
 DM_F_DISK_SYNC = 0x2
+DM_F_NUMA_LOCAL = 0x4
 DM_ING_HASH_ONLY = 0x1
 DM_ING_REPLACE = 0x2
 DM_ING_FORCE_WIDE = 0x4
@@ -59,6 +60,9 @@ class DmStats(C.Structure):
         ("ring_slabs_free", C.c_uint64),
         ("open_readers", C.c_uint64),
         ("free_stream_slots", C.c_uint64),
+        ("numa_node", C.c_int64),
+        ("aliases", C.c_uint64),
+        ("suspended", C.c_uint64),
     ]
 
 
@@ -82,6 +86,7 @@ SIGNATURES = {
     "dm_engine_stats": (C.c_int, [_P, C.POINTER(DmStats)]),
     "dm_strerror": (C.c_char_p, [C.c_int]),
     "dm_last_error": (C.c_char_p, []),
+    "dm_error_detail": (C.c_int, [_P, C.c_uint64, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dm_shard_of": (C.c_uint32, [_P, C.c_uint32]),
     "dm_streams_per_warp": (C.c_uint32, [C.c_uint32]),
     "dm_stream_open": (C.c_int, [_P, _P, C.c_uint64, _U64P]),
@@ -102,6 +107,11 @@ SIGNATURES = {
     "dm_cache_close": (C.c_int, [_P, C.c_uint64]),
     "dm_cache_evict": (C.c_int, [_P, _P]),
     "dm_cache_follow": (C.c_int, [_P, _P, _U64P, _U64P]),
+    "dm_cache_alias_put": (C.c_int, [_P, C.c_char_p, _P]),
+    "dm_cache_alias_get": (C.c_int, [_P, C.c_char_p, _P]),
+    "dm_stream_suspend": (C.c_int, [_P, C.c_uint64, _U64P]),
+    "dm_stream_resume_saved": (C.c_int, [_P, _P, C.c_uint64, _U64P, _U64P]),
+    "dm_gunzip": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dm_cache_device_extents": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), _U64P, C.c_uint32]),
     "dm_ingest_device": (C.c_int, [_P, _P, _U64P, _U64P, C.c_uint32, _P, _P, _P, C.c_uint32, C.POINTER(C.c_double)]),
     "dm_manifest_parse": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(DmLayer), C.c_uint32, C.POINTER(C.c_uint32)]),
@@ -111,6 +121,10 @@ SIGNATURES = {
     "dm_synth_fill_device_many": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, _U64P, _U64P, C.c_uint32]),
     "dm_proxy_drive": (C.c_int, [_P, _P, _U64P, C.c_uint32, _P, C.c_size_t, C.c_uint32, C.c_int, C.c_int,
                                  _P, _P, C.POINTER(C.c_double)]),
+    "dm_proxy_fetch": (C.c_int, [_P, C.c_char_p, _P, C.c_uint64, _P, C.c_size_t, _P, C.POINTER(C.c_int)]),
+    "dm_proxy_request": (C.c_int, [_P, C.c_char_p, _U64P, _U64P]),
+    "dm_proxy_manifest": (C.c_int, [_P, _P, C.c_uint64, C.c_char_p, C.c_size_t, C.POINTER(DmLayer), _U64P, C.c_uint32,
+                                    C.POINTER(C.c_uint32)]),
     "dm_proxy_serve": (C.c_int, [_P, _P, C.c_uint32, _P, _U64P, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
 }
 

@@ -25,7 +25,7 @@ int dm_cache_contains(dm_engine *e, const uint8_t digest[32], uint64_t *size)
     return DM_ENOENT;
 }
 
-int dm_cache_open(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size)
+static int cache_open_impl(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size)
 {
     if (!e || !digest || !reader) return fail(DM_EINVAL, "null argument");
     Digest d;
@@ -37,7 +37,7 @@ int dm_cache_open(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint
         if (it != e->blobs.end() && it->second->in_hbm) {
             r->blob = it->second;
             r->blob->readers++;
-            r->blob->tick = ++e->tick;
+            lru_touch(e, r->blob.get());
             r->size = r->blob->size;
         }
     }
@@ -153,12 +153,17 @@ static cudaError_t window_fill(dm_engine *e, Reader *r, Window &w, uint64_t star
         if (err == cudaSuccess) err = cudaMemcpyAsync(dst, dev, l, cudaMemcpyDeviceToHost, w.b->stream);
         dst += l;
     });
+    if (err != cudaSuccess) {           // a retry must not find a partly filled window that looks valid
+        cudaStreamSynchronize(w.b->stream);
+        w.off = 0; w.len = 0; w.pending = false;
+        return err;
+    }
     w.off = start; w.len = n; w.pending = true;
     e->st_d2h += n;
     return err;
 }
 
-int dm_cache_read(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t len, size_t *nread)
+static int cache_read_impl(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t len, size_t *nread)
 {
     if (!e || (!buf && len)) return fail(DM_EINVAL, "null argument");
     std::shared_ptr<Reader> r = find_reader(e, reader);
@@ -251,7 +256,7 @@ int dm_cache_read(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t
     return rc;
 }
 
-int dm_cache_meta(dm_engine *e, uint64_t reader, char *buf, size_t cap, size_t *len)
+static int cache_meta_impl(dm_engine *e, uint64_t reader, char *buf, size_t cap, size_t *len)
 {
     if (!e || !len || (!buf && cap)) return fail(DM_EINVAL, "null argument");
     std::shared_ptr<Reader> r = find_reader(e, reader);
@@ -270,7 +275,7 @@ int dm_cache_meta(dm_engine *e, uint64_t reader, char *buf, size_t cap, size_t *
     return DM_OK;
 }
 
-int dm_cache_close(dm_engine *e, uint64_t reader)
+static int cache_close_impl(dm_engine *e, uint64_t reader)
 {
     if (!e) return fail(DM_EINVAL, "null argument");
     std::shared_ptr<Reader> r;
@@ -298,7 +303,7 @@ int dm_cache_close(dm_engine *e, uint64_t reader)
     return DM_OK;
 }
 
-int dm_cache_follow(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size_hint)
+static int cache_follow_impl(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size_hint)
 {
     if (!e || !digest || !reader) return fail(DM_EINVAL, "null argument");
     Digest d;
@@ -323,7 +328,7 @@ int dm_cache_follow(dm_engine *e, const uint8_t digest[32], uint64_t *reader, ui
     return DM_OK;
 }
 
-int dm_cache_evict(dm_engine *e, const uint8_t digest[32])
+static int cache_evict_impl(dm_engine *e, const uint8_t digest[32])
 {
     if (!e || !digest) return fail(DM_EINVAL, "null argument");
     Digest d;
@@ -337,6 +342,7 @@ int dm_cache_evict(dm_engine *e, const uint8_t digest[32])
         if (it->second->readers) return fail(DM_ESTATE, "blob has open readers");
         b = it->second;
         b->in_hbm = false;
+        lru_drop(e, b.get());
         ext.swap(b->extents);                       // under the lock (see evict_for)
         if (!b->on_disk) e->blobs.erase(it);
     }
@@ -344,7 +350,7 @@ int dm_cache_evict(dm_engine *e, const uint8_t digest[32])
     return DM_OK;
 }
 
-int dm_cache_device_extents(dm_engine *e, uint64_t reader, void **dev_ptrs, uint64_t *lens, uint32_t max_ext)
+static int cache_device_extents_impl(dm_engine *e, uint64_t reader, void **dev_ptrs, uint64_t *lens, uint32_t max_ext)
 {
     if (!e) return fail(DM_EINVAL, "null argument");
     std::shared_ptr<Reader> r = find_reader(e, reader);
@@ -360,11 +366,106 @@ int dm_cache_device_extents(dm_engine *e, uint64_t reader, void **dev_ptrs, uint
     return (int)ext.size();
 }
 
+// ---- URL -> digest aliases -----------------------------------------------------------
+// The OnRequest hook (start.go:197-200) sees a URL.  OCI URLs name the digest; HuggingFace resolve/ URLs do
+// not, so a hit needs URL (or ETag) -> digest.  In memory: one hash map.  On the disk tier: an append-only
+// text log, one "<64 hex>\t<key>\n" per put, replayed at start (later lines win) and compacted when more
+// than half of it is dead.
+
+}  // extern "C"
+
+namespace dmi {
+
+bool digest_from_hex(const char *hex, uint8_t out[32])
+{
+    auto nib = [](char c) { return c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1; };
+    for (int i = 0; i < 32; ++i) {
+        const int h = nib(hex[2 * i]);
+        if (h < 0) return false;
+        const int l = nib(hex[2 * i + 1]);
+        if (l < 0) return false;
+        out[i] = (uint8_t)(h << 4 | l);
+    }
+    return true;
+}
+
+static bool alias_key_ok(const char *key)
+{
+    if (!key || !*key) return false;
+    size_t n = 0;
+    for (const unsigned char *p = (const unsigned char *)key; *p; ++p, ++n)
+        if (*p < 0x20 || *p == 0x7f || n >= 4096) return false;      // one key per log line
+    return true;
+}
+
+void alias_load(dm_engine *e)
+{
+    if (e->cas_dir.empty()) return;
+    const std::string path = e->cas_dir + "/aliases.log";
+    size_t lines = 0;
+    if (FILE *f = fopen(path.c_str(), "r")) {
+        std::string line;
+        char buf[8192];
+        while (fgets(buf, sizeof buf, f)) {
+            line += buf;
+            if (line.empty() || line.back() != '\n') continue;        // long line: keep reading
+            line.pop_back();
+            ++lines;
+            Digest d;
+            if (line.size() > 65 && line[64] == '\t' && digest_from_hex(line.c_str(), d.b) && alias_key_ok(line.c_str() + 65))
+                e->aliases[line.substr(65)] = d;                       // a torn last line simply fails these checks
+            line.clear();
+        }
+        fclose(f);
+    }
+    if (lines > 2 * e->aliases.size() + 1024) {                        // mostly superseded entries: rewrite
+        const std::string tmp = path + ".tmp";
+        if (FILE *f = fopen(tmp.c_str(), "w")) {
+            for (auto &kv : e->aliases) fprintf(f, "%s\t%s\n", hex_of(kv.second.b, 32).c_str(), kv.first.c_str());
+            const bool ok = fflush(f) == 0;
+            fclose(f);
+            if (!ok || rename(tmp.c_str(), path.c_str()) != 0) unlink(tmp.c_str());
+        }
+    }
+    e->alias_log = fopen(path.c_str(), "a");
+}
+
+}  // namespace dmi
+
+extern "C" {
+
+int dm_cache_alias_put(dm_engine *e, const char *key, const uint8_t digest[32])
+{
+    if (!e || !digest) return fail(DM_EINVAL, "null argument");
+    if (!alias_key_ok(key)) return note_err(e, 0, fail(DM_EINVAL, "alias key must be 1..4096 bytes without control characters"));
+    Digest d;
+    memcpy(d.b, digest, 32);
+    std::lock_guard<std::mutex> g(e->alias_mu);
+    auto it = e->aliases.find(key);
+    if (it != e->aliases.end() && it->second == d) return DM_OK;      // already known: nothing to log
+    e->aliases[key] = d;
+    if (e->alias_log) {
+        const bool ok = fprintf(e->alias_log, "%s\t%s\n", hex_of(d.b, 32).c_str(), key) > 0 && fflush(e->alias_log) == 0;
+        if (!ok) return note_err(e, 0, fail(DM_EIO, "could not append to aliases.log (the alias is held in memory only)"));
+    }
+    return DM_OK;
+}
+
+int dm_cache_alias_get(dm_engine *e, const char *key, uint8_t digest_out[32])
+{
+    if (!e || !key || !digest_out) return fail(DM_EINVAL, "null argument");
+    std::lock_guard<std::mutex> g(e->alias_mu);
+    auto it = e->aliases.find(key);
+    if (it == e->aliases.end()) return DM_ENOENT;
+    memcpy(digest_out, it->second.b, 32);
+    return DM_OK;
+}
+
 // ---- device-resident ingest -------------------------------------------------------
 
-int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets, const uint64_t *lengths,
-                     uint32_t n, const uint8_t *expect, uint8_t *digests_out, uint8_t *matched_out,
-                     uint32_t flags, double *kernel_ms)
+static int ingest_device_impl(dm_engine *e, const void *dev_base, const uint64_t *offsets, const uint64_t *lengths,
+                              uint32_t n, const uint8_t *expect, uint8_t *digests_out, uint8_t *matched_out,
+                              uint32_t flags, double *kernel_ms)
 {
     if (!e || ((!offsets || !lengths || !dev_base) && n)) return fail(DM_EINVAL, "null argument");
     if (kernel_ms) *kernel_ms = 0.0;
@@ -416,7 +517,9 @@ int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets
     if (flags & DM_ING_SPW_MASK) spw = 1 << (((flags & DM_ING_SPW_MASK) >> DM_ING_SPW_SHIFT) - 1);
     std::vector<uint32_t> order(n);
     for (uint32_t i = 0; i < n; ++i) order[i] = i;
-    if (spw > 1) {
+    bool sorted = true;                                  // equal-sized batches (the common bulk case) need no reordering
+    for (uint32_t i = 1; i < n && sorted; ++i) sorted = e->ing_jobs_h[i - 1].nbytes >= e->ing_jobs_h[i].nbytes;
+    if (spw > 1 && !sorted) {
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
             return e->ing_jobs_h[a].nbytes > e->ing_jobs_h[b].nbytes; });
         std::vector<dm::HashJob> tmp(e->ing_jobs_h, e->ing_jobs_h + n);
@@ -508,6 +611,21 @@ int dm_synth_fill_device_many(dm_engine *e, uint64_t seed, uint64_t first_blob, 
     cudaFree(d_tab);
     if (err != cudaSuccess) return fail_cuda(err, "dm_synth_fill_device_many");
     return DM_OK;
+}
+
+// ---- exported wrappers: file the error text under the reader id (dm_error_detail) ----
+int dm_cache_open(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size) { return note_err(e, 0, cache_open_impl(e, digest, reader, size)); }
+int dm_cache_read(dm_engine *e, uint64_t reader, uint64_t off, void *buf, size_t len, size_t *nread) { return note_err(e, reader, cache_read_impl(e, reader, off, buf, len, nread)); }
+int dm_cache_meta(dm_engine *e, uint64_t reader, char *buf, size_t cap, size_t *len) { return note_err(e, reader, cache_meta_impl(e, reader, buf, cap, len)); }
+int dm_cache_close(dm_engine *e, uint64_t reader) { return note_err(e, reader, cache_close_impl(e, reader)); }
+int dm_cache_follow(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size_hint) { return note_err(e, 0, cache_follow_impl(e, digest, reader, size_hint)); }
+int dm_cache_evict(dm_engine *e, const uint8_t digest[32]) { return note_err(e, 0, cache_evict_impl(e, digest)); }
+int dm_cache_device_extents(dm_engine *e, uint64_t reader, void **dev_ptrs, uint64_t *lens, uint32_t max_ext) { return note_err(e, reader, cache_device_extents_impl(e, reader, dev_ptrs, lens, max_ext)); }
+int dm_ingest_device(dm_engine *e, const void *dev_base, const uint64_t *offsets, const uint64_t *lengths,
+                     uint32_t n, const uint8_t *expect, uint8_t *digests_out, uint8_t *matched_out,
+                     uint32_t flags, double *kernel_ms)
+{
+    return note_err(e, 0, ingest_device_impl(e, dev_base, offsets, lengths, n, expect, digests_out, matched_out, flags, kernel_ms));
 }
 
 }  // extern "C"

@@ -27,9 +27,42 @@
 // start.go:197-200 (hit serving); see include/demodel_b200.h.
 #include "engine_internal.hpp"
 
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
 namespace dmi {
 
 thread_local std::string g_last_error;
+
+// Socket buffer -> ring slab.  The ring is written once by the CPU and read once by the DMA engine, never
+// by a core, so an ordinary store stream costs a read-for-ownership of every destination line (3 memory
+// transfers per byte instead of 2) and evicts the proxy's working set.  Pieces of at least nt_copy_min
+// bytes go out as streaming (non-temporal) stores: tools/ubench/ntcopy.cc, +18 % (1 thread) to +55 %
+// (4 threads) on 32 KiB pieces; slower for 4 KiB pieces, hence the threshold.  The fence orders the
+// write-combining buffers before anything that can make the DMA engine read the slab.
+void ring_copy(dm_engine *e, void *dst, const void *src, size_t n)
+{
+#if defined(__x86_64__)
+    if (e->nt_copy_min && n >= e->nt_copy_min) {
+        uint8_t *d = static_cast<uint8_t *>(dst);
+        const uint8_t *s = static_cast<const uint8_t *>(src);
+        size_t head = (size_t)((16 - ((uintptr_t)d & 15)) & 15);
+        if (head) { memcpy(d, s, head); d += head; s += head; n -= head; }
+        size_t i = 0;
+        for (; i + 64 <= n; i += 64) {
+            const __m128i a = _mm_loadu_si128((const __m128i *)(s + i)), b = _mm_loadu_si128((const __m128i *)(s + i + 16));
+            const __m128i c = _mm_loadu_si128((const __m128i *)(s + i + 32)), f = _mm_loadu_si128((const __m128i *)(s + i + 48));
+            _mm_stream_si128((__m128i *)(d + i), a); _mm_stream_si128((__m128i *)(d + i + 16), b);
+            _mm_stream_si128((__m128i *)(d + i + 32), c); _mm_stream_si128((__m128i *)(d + i + 48), f);
+        }
+        if (i < n) memcpy(d + i, s + i, n - i);
+        _mm_sfence();
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
+}
 
 int fail(int code, const char *what)
 {
@@ -50,6 +83,21 @@ int fail_cuda(cudaError_t err, const char *where)
 {
     g_last_error = std::string(where) + ": " + cudaGetErrorString(err);
     return DM_ECUDA;
+}
+
+// dm_error_detail(): the text of the last failing call on a stream / reader id, readable from any thread.
+// Bounded (the oldest ids are forgotten); misses (DM_ENOENT from a lookup) are not errors worth a slot.
+int note_err(dm_engine *e, uint64_t id, int rc)
+{
+    if (rc >= 0 || !e || rc == DM_ENOENT) return rc;
+    constexpr size_t kKeep = 4096;
+    std::lock_guard<std::mutex> g(e->err_mu);
+    auto it = e->err_text.find(id);
+    if (it != e->err_text.end()) { it->second = g_last_error; return rc; }
+    if (e->err_order.size() >= kKeep) { e->err_text.erase(e->err_order.front()); e->err_order.pop_front(); }
+    e->err_text.emplace(id, g_last_error);
+    e->err_order.push_back(id);
+    return rc;
 }
 
 
@@ -74,8 +122,28 @@ void free_extents(dm_engine *e, std::vector<Extent> &ext)
     ext.clear();
 }
 
+void lru_drop(dm_engine *e, Blob *b)
+{
+    if (!b->in_lru) return;
+    (b->lru_prev ? b->lru_prev->lru_next : e->lru_head) = b->lru_next;
+    (b->lru_next ? b->lru_next->lru_prev : e->lru_tail) = b->lru_prev;
+    b->lru_prev = b->lru_next = nullptr;
+    b->in_lru = false;
+}
+
+void lru_touch(dm_engine *e, Blob *b)
+{
+    if (b->in_lru && e->lru_tail == b) return;
+    lru_drop(e, b);
+    b->lru_prev = e->lru_tail;
+    (e->lru_tail ? e->lru_tail->lru_next : e->lru_head) = b;
+    e->lru_tail = b;
+    b->in_lru = true;
+}
+
 // Evict least-recently-used unreferenced blobs until `need` bytes could fit.
-// Caller holds neither e->mu nor arena_mu.
+// Caller holds neither e->mu nor arena_mu.  The LRU list holds exactly the HBM-resident blobs, oldest
+// first, so a victim costs a walk over the pinned ones in front of it, not a scan of the whole index.
 bool evict_for(dm_engine *e, uint64_t need)
 {
     for (;;) {
@@ -83,14 +151,16 @@ bool evict_for(dm_engine *e, uint64_t need)
         std::vector<Extent> ext;
         {
             std::lock_guard<std::mutex> g(e->mu);
-            for (auto &kv : e->blobs) {
-                Blob *b = kv.second.get();
-                if (!b->in_hbm || b->readers) continue;
+            for (Blob *b = e->lru_head; b; b = b->lru_next) {
+                if (b->readers) continue;
                 if (!e->cas_dir.empty() && !b->spill_done) continue;   // not yet safe on disk
-                if (!victim || b->tick < victim->tick) victim = kv.second;
+                auto it = e->blobs.find(b->digest);
+                if (it != e->blobs.end() && it->second.get() == b) victim = it->second;
+                break;
             }
             if (!victim) return false;
             victim->in_hbm = false;
+            lru_drop(e, victim.get());
             ext.swap(victim->extents);          // taken under the lock: a re-publish may install new ones at once
             if (!victim->on_disk) e->blobs.erase(victim->digest);
         }
@@ -141,15 +211,19 @@ Slab *slab_get(dm_engine *e)
     std::unique_lock<std::mutex> g(e->slab_mu);
     if (e->slab_free.empty() && !e->stop) {
         e->st_ring_waits++;
-        // Every slab is out: some are only partly filled and held by streams waiting for their next
-        // bytes.  Ask the pump to DMA those early so they recycle (otherwise more live streams than
-        // slabs would starve — or, with one thread driving many streams, deadlock).
+        // Every slab is out.  Usually most of them are in flight to the device and come back by
+        // themselves (writers outrunning PCIe: plain back-pressure, just wait).  But if ALL of them are
+        // partly filled and held by streams waiting for their next bytes, nothing moves: more live
+        // streams than slabs would starve - or, with one thread driving many streams, deadlock.  The
+        // pump tells the two apart (slabs_returning) and recalls partial slabs only in the second case.
+        // The waiter is counted BEFORE the pump is poked: the pump acts on "asked and somebody waits",
+        // and consumes the flag when it looks.
+        e->ring_waiters++;
         { std::lock_guard<std::mutex> gw(e->work_mu); e->ring_starved.store(true); }   // under the pump's mutex: no lost wake-up
         e->work_cv.notify_one();
+        e->slab_cv.wait(g, [&] { return !e->slab_free.empty() || e->stop; });
+        e->ring_waiters--;
     }
-    e->ring_waiters++;
-    e->slab_cv.wait(g, [&] { return !e->slab_free.empty() || e->stop; });
-    e->ring_waiters--;
     if (e->slab_free.empty()) return nullptr;
     Slab *s = e->slab_free.back();
     e->slab_free.pop_back();
@@ -163,6 +237,12 @@ void slab_put(dm_engine *e, Slab *s)
         e->slab_free.push_back(s);
     }
     e->slab_cv.notify_one();
+}
+
+void slab_return(dm_engine *e, Slab *s)
+{
+    e->slabs_returning.fetch_sub(1, std::memory_order_relaxed);
+    slab_put(e, s);
 }
 
 // Give the stream a fresh slab.  The stream mutex is dropped while waiting for
@@ -187,6 +267,7 @@ void mark_dirty(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *submitted
 {
     const bool enqueue = !sp->queued;
     sp->queued = true;
+    if (submitted) e->slabs_returning.fetch_add(1, std::memory_order_relaxed);
     {
         std::lock_guard<std::mutex> g(e->work_mu);
         if (submitted) e->pending_slabs.push_back(submitted);
@@ -210,7 +291,12 @@ int dma_range(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *slab, uint6
         if (err == cudaSuccess) err = cudaMemcpyAsync(dev, src, len, cudaMemcpyHostToDevice, cs);
         src += len;
     });
-    if (err != cudaSuccess) { s->cuda_failed = true; slab_put(e, slab); return fail_cuda(err, "cudaMemcpyAsync(H2D slab)"); }
+    if (err != cudaSuccess) {
+        s->cuda_failed = true;
+        cudaStreamSynchronize(cs);      // earlier segments of this slab may still be DMA-ing out of it
+        slab_put(e, slab);
+        return fail_cuda(err, "cudaMemcpyAsync(H2D slab)");
+    }
     e->st_h2d += n;
     return DM_OK;
 }
@@ -226,7 +312,9 @@ void absorb_islands(Stream *s)
     }
 }
 
-// DMA the stream's sequential slab to its place in the blob.  Stream mutex held.
+// DMA the stream's sequential slab to its place in the blob.  Stream mutex held.  A failure drops the
+// staged bytes and is recorded in s->lost (sticky): whoever calls next - this may be the pump recalling a
+// partial slab, with no writer to tell - learns that the stream is broken, and it is never published.
 int submit_slab(dm_engine *e, const std::shared_ptr<Stream> &sp)
 {
     Stream *s = sp.get();
@@ -239,15 +327,16 @@ int submit_slab(dm_engine *e, const std::shared_ptr<Stream> &sp)
     if (s->verify_only) {
         cudaSetDevice(e->device);
         cudaError_t err = cudaMemcpyAsync(slab->dev, slab->host, n, cudaMemcpyHostToDevice, e->copy_stream[s->id % kCopyStreams]);
-        if (err != cudaSuccess) { slab_put(e, slab); return fail_cuda(err, "cudaMemcpyAsync(H2D slab)"); }
+        if (err != cudaSuccess) { slab_put(e, slab); s->cuda_failed = true; return s->lost = fail_cuda(err, "cudaMemcpyAsync(H2D slab)"); }
         e->st_h2d += n;
         s->staged.emplace_back(slab, n);
+        e->slabs_returning.fetch_add(1, std::memory_order_relaxed);
         s->dma_issued += n;
         mark_dirty(e, sp, nullptr);       // the slab stays out of the ring until its job has run
         return DM_OK;
     }
     int rc = dma_range(e, sp, slab, s->dma_issued, n);
-    if (rc != DM_OK) return rc;
+    if (rc != DM_OK) return s->lost = rc;      // the staged bytes are gone: the stream can only be aborted now
     s->dma_issued += n;
     absorb_islands(s);
     mark_dirty(e, sp, slab);
@@ -264,7 +353,7 @@ int submit_part(dm_engine *e, const std::shared_ptr<Stream> &sp, size_t idx)
     if (pt.fill == 0) { slab_put(e, pt.slab); return DM_OK; }
     e->st_ingested.fetch_add(pt.fill, std::memory_order_relaxed);
     int rc = dma_range(e, sp, pt.slab, pt.base, pt.fill);
-    if (rc != DM_OK) return rc;
+    if (rc != DM_OK) return s->lost = rc;
     if (pt.base + pt.fill <= s->resume_base) add_interval(s->prefix_cover, pt.base, pt.base + pt.fill);
     else add_interval(s->islands, pt.base, pt.base + pt.fill);
     absorb_islands(s);
@@ -358,15 +447,15 @@ std::shared_ptr<Blob> publish(dm_engine *e, const Digest &d, uint64_t size, std:
         auto it = e->blobs.find(d);
         if (it != e->blobs.end() && it->second->in_hbm) {
             b = it->second;
-            b->tick = ++e->tick;
+            lru_touch(e, b.get());
         } else if (it != e->blobs.end()) {   // known on disk only: re-home into HBM
             b = it->second;
             b->extents = kept; kept.clear();
-            b->in_hbm = true; b->tick = ++e->tick;
+            b->in_hbm = true; lru_touch(e, b.get());
         } else {
             b = std::make_shared<Blob>();
             b->digest = d; b->size = size; b->extents = kept; kept.clear();
-            b->in_hbm = true; b->tick = ++e->tick;
+            b->in_hbm = true; lru_touch(e, b.get());
             if (meta) b->meta.swap(*meta);
             e->blobs[d] = b;
             fresh = true;
@@ -393,19 +482,20 @@ void publish_many(dm_engine *e, const std::vector<Verified> &items)
     std::vector<std::shared_ptr<Blob>> to_spill;
     {
         std::lock_guard<std::mutex> g(e->mu);
+        e->blobs.reserve(e->blobs.size() + items.size());           // one rehash, not log(n) of them
         for (const Verified &v : items) {
             auto it = e->blobs.find(v.d);
             if (it != e->blobs.end() && it->second->in_hbm) {          // an earlier copy wins
-                it->second->tick = ++e->tick;
+                lru_touch(e, it->second.get());
                 to_free.push_back(v.x);
             } else if (it != e->blobs.end()) {                         // on disk only: re-home
                 Blob *b = it->second.get();
                 b->extents.assign(1, v.x);
-                b->in_hbm = true; b->tick = ++e->tick;
+                b->in_hbm = true; lru_touch(e, b);
             } else {
                 auto b = std::make_shared<Blob>();
                 b->digest = v.d; b->size = v.size; b->extents.assign(1, v.x);
-                b->in_hbm = true; b->tick = ++e->tick;
+                b->in_hbm = true; lru_touch(e, b.get());
                 e->blobs.emplace(v.d, b);
                 if (!e->cas_dir.empty()) to_spill.push_back(b);
             }
@@ -437,6 +527,7 @@ void evict_many(dm_engine *e, const uint8_t *digests, uint32_t n)
             auto it = e->blobs.find(d);
             if (it == e->blobs.end() || !it->second->in_hbm || it->second->readers) continue;
             it->second->in_hbm = false;
+            lru_drop(e, it->second.get());
             ext.insert(ext.end(), it->second->extents.begin(), it->second->extents.end());
             it->second->extents.clear();            // under the lock (see evict_for)
             if (!it->second->on_disk) e->blobs.erase(it);
@@ -460,7 +551,7 @@ void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint
     if (s->st == St::Aborted) return;
     words_to_digest(words, s->digest.b);
     s->matched = (!s->has_expect || s->digest == s->expect) ? 1 : 0;
-    if (s->cuda_failed) { s->matched = 0; memset(s->digest.b, 0, 32); }     // never publish under a digest the device may not have produced
+    if (s->cuda_failed || s->lost != DM_OK) { s->matched = 0; memset(s->digest.b, 0, 32); }     // never publish under a digest the device may not have produced, or a body with bytes missing
     s->completing = true;                       // no new follower copy-out starts past this point
     wait_follow_reads(s, g);
     std::vector<Extent> ext;
@@ -486,6 +577,22 @@ void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint
     s->cv.notify_all();
 }
 
+void completer_main(dm_engine *e)
+{
+    cudaSetDevice(e->device);
+    for (;;) {
+        dm_engine::DoneItem it;
+        {
+            std::unique_lock<std::mutex> g(e->done_mu);
+            e->done_cv.wait(g, [&] { return !e->done_q.empty() || e->done_stop; });
+            if (e->done_q.empty()) return;
+            it = std::move(e->done_q.front());
+            e->done_q.pop_front();
+        }
+        complete_stream(e, it.sp, it.words);
+    }
+}
+
 void reap_cycle(dm_engine *e, Cycle &c)
 {
     float ms = 0.f;
@@ -495,7 +602,7 @@ void reap_cycle(dm_engine *e, Cycle &c)
         e->st_kernel_ms += ms;
     }
     e->st_hashed += c.bytes;
-    for (Slab *sl : c.job_slabs) if (sl) slab_put(e, sl);
+    for (Slab *sl : c.job_slabs) if (sl) slab_return(e, sl);
     c.job_slabs.clear();
     for (size_t i = 0; i < c.streams.size(); ++i) {
         std::shared_ptr<Stream> &sp = c.streams[i];
@@ -516,7 +623,11 @@ void reap_cycle(dm_engine *e, Cycle &c)
             std::lock_guard<std::mutex> g(e->mu);
             e->free_slots.push_back(sp->slot);
         } else if (c.is_final[i]) {
-            complete_stream(e, sp, e->h_digests + 8ull * sp->slot);
+            dm_engine::DoneItem it;
+            it.sp = sp;
+            memcpy(it.words, e->h_digests + 8ull * sp->slot, sizeof it.words);
+            { std::lock_guard<std::mutex> g(e->done_mu); e->done_q.push_back(std::move(it)); }
+            e->done_cv.notify_one();
         }
     }
     c.streams.clear(); c.is_final.clear();
@@ -529,9 +640,25 @@ void reap_cycle(dm_engine *e, Cycle &c)
 bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &ready)
 {
     c.njobs = 0; c.bytes = 0;
-    // One slab per job: a launch lasts as long as its longest lane, so lanes are kept the same
-    // length (streams holding more simply go again in the next launch, which overlaps this one).
-    const uint64_t quantum = (uint64_t)e->cfg.slab_bytes;
+    // Job length.  A launch is reaped as a whole, so it lasts as long as its longest lane and every lane
+    // should be the same length: the quantum.  It is one slab while the streams are network-bound (each has
+    // about a slab of backlog when it becomes ready), and grows to the smallest backlog among the streams
+    // that are at least a slab behind, up to kMaxJobSlabs slabs, when the hash is the bottleneck (few
+    // streams, DMA far ahead): fewer, longer launches, so the reap -> rebuild -> relaunch gap between two jobs
+    // of a stream (host work, ~0.1 ms) is paid once per 8 MiB instead of once per MiB.
+    const uint64_t slab = (uint64_t)e->cfg.slab_bytes;
+    uint64_t quantum = slab;
+    {
+        uint64_t min_backlog = ~0ull;
+        for (auto &sp : ready) {
+            Stream *s = sp.get();
+            std::lock_guard<std::mutex> g(s->mu);
+            if (s->st == St::Aborted || s->st == St::Done || s->final_issued || s->jobs_inflight || s->verify_only) continue;
+            const uint64_t backlog = s->dma_issued - s->hash_issued;
+            if (backlog >= slab) min_backlog = std::min(min_backlog, backlog);
+        }
+        if (min_backlog != ~0ull) quantum = std::min<uint64_t>(min_backlog / slab, kMaxJobSlabs) * slab;
+    }
     std::vector<std::shared_ptr<Stream>> again;
     for (auto &sp : ready) {
         Stream *s = sp.get();
@@ -632,9 +759,15 @@ void flush_partial_slabs(dm_engine *e)
         Stream *s = sp.get();
         std::unique_lock<std::mutex> g(s->mu, std::try_to_lock);
         if (!g.owns_lock() || s->st != St::Open || s->window_out) continue;
+        // A submit that fails here (arena full while growing an unknown-size body, a failed copy) has
+        // already dropped the staged bytes, and the writer is not on this thread to be told: remember it
+        // in the stream, so that its next write / finish / checkpoint fails and nothing is ever published.
+        auto lose = [&](int rc) {
+            if (rc != DM_OK && s->lost == DM_OK) { s->lost = rc; s->cv.notify_all(); }
+        };
         // a part that was sent early simply becomes an island; the range continues in a fresh part
         for (size_t i = s->parts.size(); i-- > 0;)
-            if (s->parts[i].fill) submit_part(e, sp, i);
+            if (s->parts[i].fill) lose(submit_part(e, sp, i));
         if (!s->cur || s->cur_fill == 0) continue;
         if (s->verify_only && (s->cur_fill & 63)) {              // slab-by-slab hashing needs whole blocks:
             const uint32_t whole = s->cur_fill & ~63u;           // send those, keep the tail in the stream
@@ -642,7 +775,7 @@ void flush_partial_slabs(dm_engine *e)
             memcpy(s->carry, s->cur->host + whole, s->carry_fill);
             s->cur_fill = whole;                                 // (0 whole blocks: submit_slab just returns the slab)
         }
-        submit_slab(e, sp);
+        lose(submit_slab(e, sp));
     }
 }
 
@@ -670,14 +803,18 @@ void pump_main(dm_engine *e)
             bool done = true;
             for (int i = 0; i < kCopyStreams; ++i) done = done && poll_event(b.ev[i]) == cudaSuccess;
             if (!done) break;
-            for (Slab *sl : b.slabs) slab_put(e, sl);
+            for (Slab *sl : b.slabs) slab_return(e, sl);
             b.slabs.clear(); b.busy = false;
             b_tail = (b_tail + 1) % kSlabBatches; --b_live;
         }
-        // a recall can miss slabs (stream busy in a write, window lent out): repeat while writers wait
-        if (e->ring_starved.exchange(false) || (e->ring_waiters.load() > 0 && ++starve_ticks >= 16)) {
-            starve_ticks = 0;
-            flush_partial_slabs(e);
+        // Writers blocked on the ring: recall partly filled slabs only when nothing is on its way back
+        // (see slabs_returning).  A recall can miss slabs (stream busy in a write, window lent out), so it
+        // is repeated every 16 passes while the writers are still waiting and still nothing is in flight.
+        {
+            const bool asked = e->ring_starved.exchange(false);
+            if (e->ring_waiters.load() > 0 && e->slabs_returning.load() == 0) {
+                if (asked || ++starve_ticks >= 16) { starve_ticks = 0; flush_partial_slabs(e); }
+            } else starve_ticks = asked ? 15 : 0;      // re-check on the very next pass if somebody just asked
         }
         // 2. finished hash launches (any order)
         bool reaped = false;
@@ -767,21 +904,18 @@ void mkdirs(const std::string &path)
         if (path[i] == '/') { std::string p = path.substr(0, i); mkdir(p.c_str(), 0755); }
 }
 
-bool spill_one(dm_engine *e, Blob *b)
+// Write the first `size` bytes held in `ext` to `fd` through two pinned buffers: the D2H of piece k+1 runs
+// while piece k is written to the file.  Used by the disk tier (spill) and by dm_stream_suspend.
+bool d2h_to_fd(dm_engine *e, const std::vector<Extent> &ext, uint64_t size, int fd)
 {
-    const std::string path = blob_path(e, b->digest.b), tmp = path + ".part";
-    mkdirs(path);
-    int fd = open(tmp.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
-    if (fd < 0) return false;
-    // two pinned buffers: the D2H of piece k+1 runs while piece k is written to the file
     Bounce *bn[2] = {bounce_get(e), bounce_get(e)};
     uint64_t piece_len[2] = {0, 0};
     bool ok = true;
     auto start_piece = [&](int slot, uint64_t off) {
-        const uint64_t n = std::min<uint64_t>(kBounceBytes, b->size - off);
+        const uint64_t n = std::min<uint64_t>(kBounceBytes, size - off);
         uint8_t *dst = bn[slot]->host;
         cudaError_t err = cudaSuccess;
-        for_segments(e, b->extents, off, n, [&](uint8_t *dev, uint64_t len) {
+        for_segments(e, ext, off, n, [&](uint8_t *dev, uint64_t len) {
             if (err == cudaSuccess) err = cudaMemcpyAsync(dst, dev, len, cudaMemcpyDeviceToHost, bn[slot]->stream);
             dst += len;
         });
@@ -790,9 +924,9 @@ bool spill_one(dm_engine *e, Blob *b)
     };
     uint64_t issued = 0, written = 0;
     int cur = 0;
-    if (b->size) { ok = start_piece(0, 0); issued = piece_len[0]; }
-    while (ok && written < b->size) {
-        if (issued < b->size) { ok = start_piece(cur ^ 1, issued); issued += piece_len[cur ^ 1]; }
+    if (size) { ok = start_piece(0, 0); issued = piece_len[0]; }
+    while (ok && written < size) {
+        if (issued < size) { ok = start_piece(cur ^ 1, issued); issued += piece_len[cur ^ 1]; }
         if (cudaStreamSynchronize(bn[cur]->stream) != cudaSuccess) { ok = false; break; }
         const uint64_t n = piece_len[cur];
         e->st_d2h += n;
@@ -809,6 +943,16 @@ bool spill_one(dm_engine *e, Blob *b)
     cudaStreamSynchronize(bn[1]->stream);
     bounce_put(e, bn[0]);
     bounce_put(e, bn[1]);
+    return ok;
+}
+
+bool spill_one(dm_engine *e, Blob *b)
+{
+    const std::string path = blob_path(e, b->digest.b), tmp = path + ".part";
+    mkdirs(path);
+    int fd = open(tmp.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+    if (fd < 0) return false;
+    bool ok = d2h_to_fd(e, b->extents, b->size, fd);
     close(fd);
     if (ok) ok = rename(tmp.c_str(), path.c_str()) == 0;
     if (ok) write_sidecar(path + ".meta", *b);
@@ -872,13 +1016,18 @@ std::shared_ptr<Stream> find_stream(dm_engine *e, uint64_t id)
 void drop_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, bool release_slot)
 {
     const int k = (int)(sp->id % kStripes);
+    bool erased;
     {
         std::lock_guard<std::mutex> g(e->stripe_mu[k]);
-        if (e->streams[k].erase(sp->id)) e->n_streams--;
+        erased = e->streams[k].erase(sp->id) != 0;
+        if (erased) e->n_streams--;
     }
     {
         std::lock_guard<std::mutex> g(e->mu);
-        if (release_slot) e->free_slots.push_back(sp->slot);
+        // exactly one caller takes the stream out of the table, and only that one may give its state slot
+        // back (two finishes on one id, or a finish racing an abort, would otherwise release it twice and
+        // two later streams would share one state / digest slot)
+        if (release_slot && erased) e->free_slots.push_back(sp->slot);
         if (sp->has_expect) {
             auto it = e->inflight.find(sp->expect);
             if (it != e->inflight.end() && (it->second.expired() || it->second.lock() == sp)) e->inflight.erase(it);
@@ -890,8 +1039,14 @@ int ensure_ingest_scratch(dm_engine *e, uint32_t n)
 {
     if (n <= e->ing_cap) return DM_OK;
     const uint32_t cap = std::max<uint32_t>(n, 4096);
-    if (e->ing_states) { cudaFree(e->ing_states); cudaFree(e->ing_digests); cudaFree(e->ing_jobs_d);
-                         cudaFreeHost(e->ing_jobs_h); cudaFreeHost(e->ing_digests_h); e->ing_cap = 0; }
+    // free and forget: if one of the allocations below fails, the next call (or dm_engine_destroy) must not
+    // free these a second time
+    e->ing_cap = 0;
+    if (e->ing_states) { cudaFree(e->ing_states); e->ing_states = nullptr; }
+    if (e->ing_digests) { cudaFree(e->ing_digests); e->ing_digests = nullptr; }
+    if (e->ing_jobs_d) { cudaFree(e->ing_jobs_d); e->ing_jobs_d = nullptr; }
+    if (e->ing_jobs_h) { cudaFreeHost(e->ing_jobs_h); e->ing_jobs_h = nullptr; }
+    if (e->ing_digests_h) { cudaFreeHost(e->ing_digests_h); e->ing_digests_h = nullptr; }
     CU_TRY(cudaMalloc(&e->ing_states, 32ull * cap));
     CU_TRY(cudaMalloc(&e->ing_digests, 32ull * cap));
     CU_TRY(cudaMalloc(&e->ing_jobs_d, sizeof(dm::HashJob) * (uint64_t)cap));

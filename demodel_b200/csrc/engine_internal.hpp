@@ -42,6 +42,10 @@ using dm::add_interval;
 
 extern thread_local std::string g_last_error;      // what dm_last_error() returns (engine_core.cu)
 int fail(int code, const char *what);
+// Record the calling thread's detail text under a stream / reader id (0 = engine-level call) when rc is an
+// error, so that dm_error_detail() can return it from ANY thread (cgo: a goroutine may change OS threads
+// between the failing call and the call that asks for the text).  Returns rc.
+int note_err(dm_engine *e, uint64_t id, int rc);
 cudaError_t poll_event(cudaEvent_t ev);
 int fail_cuda(cudaError_t err, const char *where);
 #define CU_TRY(expr)                                                   \
@@ -53,12 +57,14 @@ int fail_cuda(cudaError_t err, const char *where);
 constexpr uint64_t kAlign = 256;           // CAS extent granularity
 constexpr uint64_t kMaxGrow = 256ull << 20;
 constexpr int kCycles = 8;                 // concurrent hash launches, each on its own CUDA stream
+constexpr uint32_t kMaxJobSlabs = 8;       // a job covers 1..8 slabs of backlog (run_cycle): fewer, longer launches when the hash is behind
 constexpr int kSlabBatches = 64;           // groups of DMA'd slabs waiting for their copy events
 constexpr int kStripes = 64;               // stream-table lock stripes
 constexpr int kCopyStreams = 2;
 constexpr size_t kBounceBytes = 4u << 20;
 constexpr int kBounces = 48;               // 4 MiB each; readers borrow two as read-ahead windows
 constexpr int kSpillThreads = 4;           // disk-tier writers (each double-buffers two bounce buffers)
+constexpr int kCompleters = 2;             // threads that compare / publish finished bodies, so the pump only launches and reaps
 constexpr int kBounceReserve = 2 * kSpillThreads + 2;          // never lent to windows: the spill thread and one-shot reads need some
 
 inline uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
@@ -99,7 +105,8 @@ struct Blob {
     uint64_t size = 0;
     std::vector<Extent> extents;          // empty once evicted from HBM
     uint32_t readers = 0;
-    uint64_t tick = 0;
+    Blob *lru_prev = nullptr, *lru_next = nullptr;   // intrusive LRU links while in_hbm (guarded by e->mu): no node allocation
+    bool in_lru = false;
     bool in_hbm = false;
     bool on_disk = false;
     bool spill_done = false;
@@ -155,7 +162,8 @@ struct Stream {
     Digest digest{};
     int matched = 0;
     bool cuda_failed = false;  // a copy or launch for this stream failed: whatever digest comes back is not trusted
-    int result = DM_OK;
+    int lost = DM_OK;          // sticky: bytes this stream had accepted were dropped by a pump-side submit (arena full while
+                               // recalling a partial slab ...).  write / finish / checkpoint return it; never published.
     std::shared_ptr<Blob> blob;   // set at commit
 };
 
@@ -206,6 +214,7 @@ struct dm_engine {
     std::string cas_dir;
     int device = 0;
     int sm_count = 148;
+    int numa_node = -1;              // DM_F_NUMA_LOCAL: the node the engine bound itself to, -1 = not bound
     int force_spw = 0;               // DM_FORCE_SPW: 1/2/4/8/16/32 streams per warp for every launch (tuning only)
     int variant_wide = dm::kDefaultWideVariant, variant_deep = dm::kDefaultDeepVariant;   // DM_KERNEL_VARIANT overrides (tuning only)
 
@@ -238,18 +247,36 @@ struct dm_engine {
     std::unordered_map<Digest, std::weak_ptr<Stream>, DigestHash> inflight;   // open streams by expected digest
     std::mutex reader_mu[kStripes];
     std::unordered_map<uint64_t, std::shared_ptr<Reader>> readers[kStripes];
-    uint64_t tick = 0;
+    Blob *lru_head = nullptr, *lru_tail = nullptr;   // HBM-resident blobs, least recently used first (guarded by mu):
+                                                     // eviction walks from the head instead of scanning the whole index
 
     std::mutex work_mu;              // pump inbox
     std::condition_variable work_cv;
     std::vector<std::shared_ptr<Stream>> dirty;
     std::vector<Slab *> pending_slabs;
     std::atomic<bool> stop{false};   // set under work_mu; the spill threads read it under spill_mu
-    std::atomic<int> ring_waiters{0};   // writers blocked in slab_get(): the pump keeps recalling partial slabs meanwhile
+    std::atomic<int> ring_waiters{0};   // writers blocked in slab_get()
+    // Slabs that are out of the ring but come back WITHOUT any writer doing anything: handed to the pump
+    // with their DMA enqueued (returned when the copy event fires) or staged by a verify-only stream
+    // (returned when their job has run).  While this is non-zero a blocked writer only has to wait; the pump
+    // recalls partly filled slabs from other streams only when it is zero, i.e. when every slab is being
+    // filled by somebody and nothing would otherwise move (more live streams than slabs).
+    std::atomic<int> slabs_returning{0};
+    uint32_t nt_copy_min = 0;           // dm_stream_write pieces >= this many bytes use streaming stores (0 = never)
     std::thread pump;
     Cycle cycles[kCycles];
     SlabBatch batches[kSlabBatches];
     uint32_t max_jobs = 0;
+
+    // Finished bodies (final job reaped, digest words copied out) waiting to be compared with their expected
+    // digest and published: index and arena work that would otherwise sit on the single pump thread and cap
+    // small-body throughput.
+    struct DoneItem { std::shared_ptr<Stream> sp; uint32_t words[8]; };
+    std::mutex done_mu;
+    std::condition_variable done_cv;
+    std::deque<DoneItem> done_q;
+    bool done_stop = false;
+    std::vector<std::thread> completers;
 
     std::mutex spill_mu;
     std::condition_variable spill_cv, spill_done_cv;
@@ -273,6 +300,15 @@ struct dm_engine {
     uint32_t *ing_digests_h = nullptr;     // pinned
     uint32_t ing_cap = 0;
     cudaEvent_t ing_ev0{}, ing_ev1{};
+
+    std::mutex alias_mu;             // URL / ETag -> digest (dm_cache_alias_put/get); log = <cas_dir>/aliases.log
+    std::unordered_map<std::string, Digest> aliases;
+    FILE *alias_log = nullptr;
+    std::atomic<uint64_t> n_suspended{0};   // *.ckpt under <cas_dir>/partial
+
+    std::mutex err_mu;               // dm_error_detail(): last error text by stream / reader id (bounded)
+    std::unordered_map<uint64_t, std::string> err_text;
+    std::deque<uint64_t> err_order;
 
     // stats
     // the two counters bumped from caller threads sit on cache lines of their own (many writers / readers at once)
@@ -309,10 +345,14 @@ void for_segments(dm_engine *e, const std::vector<Extent> &ext, uint64_t off, ui
 uint8_t *seg_at(dm_engine *e, const std::vector<Extent> &ext, uint64_t off, uint64_t *contig);
 void free_extents(dm_engine *e, std::vector<Extent> &ext);
 bool evict_for(dm_engine *e, uint64_t need);
+void lru_touch(dm_engine *e, Blob *b);        // e->mu held: (re)insert as most recently used
+void lru_drop(dm_engine *e, Blob *b);         // e->mu held: the blob left HBM
 bool arena_alloc(dm_engine *e, uint64_t len, Extent *out);
 int ensure_capacity(dm_engine *e, Stream *s, uint64_t need);
 Slab *slab_get(dm_engine *e);
 void slab_put(dm_engine *e, Slab *s);
+void slab_return(dm_engine *e, Slab *s);      // slab_put for a slab that was counted in slabs_returning
+void ring_copy(dm_engine *e, void *dst, const void *src, size_t n);   // socket buffer -> ring slab
 int take_slab(dm_engine *e, Stream *s, std::unique_lock<std::mutex> &g);
 void mark_dirty(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *submitted);
 int dma_range(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *slab, uint64_t base, uint32_t n);
@@ -331,6 +371,7 @@ void publish_many(dm_engine *e, const std::vector<Verified> &items);
 void evict_many(dm_engine *e, const uint8_t *digests, uint32_t n);
 void wait_follow_reads(Stream *s, std::unique_lock<std::mutex> &g);
 void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint32_t *words);
+void completer_main(dm_engine *e);
 void reap_cycle(dm_engine *e, Cycle &c);
 bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &ready);
 void flush_partial_slabs(dm_engine *e);
@@ -339,11 +380,14 @@ Bounce *bounce_get(dm_engine *e);
 Bounce *bounce_try_get(dm_engine *e);     // for long-lived borrowers: leaves a reserve
 void bounce_put(dm_engine *e, Bounce *b);
 void mkdirs(const std::string &path);
+bool d2h_to_fd(dm_engine *e, const std::vector<Extent> &ext, uint64_t size, int fd);
 bool spill_one(dm_engine *e, Blob *b);
 void spill_main(dm_engine *e);
 int ensure_dev_ring(dm_engine *e);
 std::shared_ptr<Stream> find_stream(dm_engine *e, uint64_t id);
 void drop_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, bool release_slot);
 int ensure_ingest_scratch(dm_engine *e, uint32_t n);
+void alias_load(dm_engine *e);                // dm_engine_create: replay <cas_dir>/aliases.log
+bool digest_from_hex(const char *hex, uint8_t out[32]);
 
 }  // namespace dmi

@@ -27,7 +27,7 @@ struct MemUpstream : dm::Upstream {
     long Read(void *dst, size_t n) override
     {
         if (n > left) n = (size_t)left;
-        memcpy(dst, p, n);
+        if (n) memcpy(dst, p, n);
         p += n; left -= n;
         return (long)n;
     }
@@ -171,4 +171,61 @@ extern "C" int dm_proxy_serve(dm_engine *e, const uint8_t *digests, uint32_t n, 
     for (auto &t : th) t.join();
     if (seconds) *seconds = now_s() - t0;
     return first_err.load();
+}
+
+// ---- single-connection twins of the two hooks, for callers (tests) that work with URLs ----------------
+
+// OnResponse for one body fetched under `url`: tee it into the engine in `chunk`-byte reads.  expect may be
+// NULL (HuggingFace resolve/ URL: digest unknown until hashed); a verified body is entered in the alias
+// index under the URL.
+extern "C" int dm_proxy_fetch(dm_engine *e, const char *url, const void *body, uint64_t len, const uint8_t *expect,
+                              size_t chunk, uint8_t digest_out[32], int *matched_out)
+{
+    if (!e || (!body && len)) return DM_EINVAL;
+    if (chunk == 0) chunk = 32768;
+    MemUpstream up(static_cast<const uint8_t *>(body), len);
+    dm::BodyTee tee(e, &up, expect, len);
+    if (tee.status() != DM_OK) return tee.status();
+    tee.SetURL(url);
+    std::vector<uint8_t> buf(chunk);
+    long got;
+    while ((got = tee.Read(buf.data(), chunk)) > 0) {}
+    if (got < 0) return (int)got;
+    if (digest_out) memcpy(digest_out, tee.digest(), 32);
+    if (matched_out) *matched_out = tee.matched() ? 1 : 0;
+    return tee.status();
+}
+
+// OnRequest: does this URL name something in the cache?  DM_ENOENT = miss (go upstream); DM_OK = *reader is
+// an open cache reader (dm_cache_read / dm_cache_close) over *size bytes.
+extern "C" int dm_proxy_request(dm_engine *e, const char *url, uint64_t *reader, uint64_t *size)
+{
+    if (!e || !url || !reader) return DM_EINVAL;
+    dm::HitReader hr(e, url);
+    if (!hr.hit()) return DM_ENOENT;
+    if (size) *size = hr.size();
+    *reader = hr.Release();
+    return DM_OK;
+}
+
+// OnResponse for a manifest body (possibly Content-Encoding: gzip): pass it through in `chunk` reads, then
+// parse and prefetch.  layers_out / ids_out receive up to max_layers entries, *n_layers the count found.
+extern "C" int dm_proxy_manifest(dm_engine *e, const void *body, uint64_t len, const char *content_encoding, size_t chunk,
+                                 dm_layer *layers_out, uint64_t *ids_out, uint32_t max_layers, uint32_t *n_layers)
+{
+    if (!e || (!body && len) || !n_layers) return DM_EINVAL;
+    if (chunk == 0) chunk = 32768;
+    MemUpstream up(static_cast<const uint8_t *>(body), len);
+    dm::ManifestTee tee(e, &up, content_encoding);
+    std::vector<uint8_t> buf(chunk);
+    uint64_t seen = 0;
+    long got;
+    while ((got = tee.Read(buf.data(), chunk)) > 0) seen += (uint64_t)got;      // goproxy's copy loop: bytes reach the client unchanged
+    if (got < 0 || seen != len) return DM_EIO;
+    *n_layers = (uint32_t)tee.layers().size();
+    for (uint32_t i = 0; i < *n_layers && i < max_layers; ++i) {
+        if (layers_out) layers_out[i] = tee.layers()[i];
+        if (ids_out) ids_out[i] = tee.ids()[i];
+    }
+    return tee.status();
 }

@@ -613,6 +613,9 @@ cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *st
     case 1: case 3: sha256_deep_kernel<1><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     case 2: sha256_deep_kernel<2><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     case 4: sha256_deep_kernel<4><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 5: sha256_deep_kernel<5><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 6: sha256_deep_kernel<6><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 7: sha256_deep_kernel<7><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     default: sha256_deep_kernel<0><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     }
     return cudaGetLastError();
@@ -640,8 +643,13 @@ cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *s
 {
     if (njobs == 0) return cudaSuccess;
     clear_stale_error();
-    return variant == 4 ? launch_group_t<4>(jobs, njobs, states, digests, stream, streams_per_warp)
-                        : launch_group_t<0>(jobs, njobs, states, digests, stream, streams_per_warp);
+    switch (variant) {
+    case 4: return launch_group_t<4>(jobs, njobs, states, digests, stream, streams_per_warp);
+    case 5: return launch_group_t<5>(jobs, njobs, states, digests, stream, streams_per_warp);
+    case 6: return launch_group_t<6>(jobs, njobs, states, digests, stream, streams_per_warp);
+    case 7: return launch_group_t<7>(jobs, njobs, states, digests, stream, streams_per_warp);
+    default: return launch_group_t<0>(jobs, njobs, states, digests, stream, streams_per_warp);
+    }
 }
 
 cudaError_t launch_synth_fill(uint64_t seed, uint64_t blob, uint64_t byte_off, void *dst, size_t len,

@@ -38,7 +38,7 @@ cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *st
                                uint32_t *digests, cudaStream_t stream, int variant);
 constexpr int kDefaultWideVariant = 9;   // fma 1 + style 2
 // S streams per warp, S in {2,4,8,16}: the middle ground between deep and wide.  `variant` is the deep
-// kernel's (the serial phase is the same code): 4 = short-chain round, anything else = ptxas' ordering.
+// kernel's (the serial phase is the same code): 4..7 = the short-chain rounds, anything else = ptxas' ordering.
 cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *states,
                                 uint32_t *digests, cudaStream_t stream, int streams_per_warp, int variant);
 
@@ -53,7 +53,9 @@ inline int streams_per_warp_for(uint32_t njobs)
     if (njobs <= 12288) return 16;
     return 32;
 }
-constexpr int kDefaultDeepVariant = 0;
+// 7 = short-chain round with e' on the FMA pipe and a' as one IADD3 (sha256_round.cuh): measured on B200
+// 256 x 8 MiB: variant 0 132.2 ms, 4 120.6, 5 119.1, 6 119.5, 7 110.7 (profiles/r02_round_variants.txt).
+constexpr int kDefaultDeepVariant = 7;
 
 
 cudaError_t launch_synth_fill(uint64_t seed, uint64_t blob, uint64_t byte_off, void *dst,

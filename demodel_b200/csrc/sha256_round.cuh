@@ -100,7 +100,7 @@ struct FmaK {
 template <int kFma>
 DM_RD uint32_t addf(uint32_t a, uint32_t b, const FmaK &k)
 {
-    if constexpr (kFma == 0 || kFma == 4) {
+    if constexpr (kFma == 0 || kFma >= 4) {      // 4..7: round forms of their own; other additions left to ptxas
         (void)k;
         return a + b;
     } else {
@@ -136,6 +136,32 @@ DM_RD void sha_round(uint32_t (&v)[8], uint32_t kw, const FmaK &k)
         const uint32_t dx = mad32(mad32(v[ih], k.one, kw), k.one, v[id]);
         const uint32_t md = mad32(v[id], k.neg, f_maj(v[ia], v[ib], v[ic]));
         const uint32_t en = add3(dx, f_ch(v[ie], v[jf], v[ig]), big_sigma1(v[ie]));
+        v[ih] = add3(md, big_sigma0(v[ia]), en);
+        v[id] = en;
+    } else if constexpr (kFma == 5) {
+        // 10 ALU-pipe instructions (6 SHF + 4 LOP3), every addition an IMAD: 20 cycles of ALU issue per round.
+        // Each chain still ends one instruction after its LOP3:  e' = S1 + (Ch + dx),  a' = S0 + (e' + md).
+        const uint32_t dx = mad32(mad32(v[ih], k.one, kw), k.one, v[id]);
+        const uint32_t md = mad32(v[id], k.neg, f_maj(v[ia], v[ib], v[ic]));
+        const uint32_t cx = mad32(f_ch(v[ie], v[jf], v[ig]), k.one, dx);
+        const uint32_t en = mad32(big_sigma1(v[ie]), k.one, cx);
+        const uint32_t tm = mad32(en, k.one, md);
+        v[ih] = mad32(big_sigma0(v[ia]), k.one, tm);
+        v[id] = en;
+    } else if constexpr (kFma == 6) {
+        // e' on the ALU pipe (one IADD3, shortest e-chain), a' on the FMA pipe: 11 ALU-pipe instructions.
+        const uint32_t dx = mad32(mad32(v[ih], k.one, kw), k.one, v[id]);
+        const uint32_t md = mad32(v[id], k.neg, f_maj(v[ia], v[ib], v[ic]));
+        const uint32_t en = add3(dx, f_ch(v[ie], v[jf], v[ig]), big_sigma1(v[ie]));
+        const uint32_t tm = mad32(en, k.one, md);
+        v[ih] = mad32(big_sigma0(v[ia]), k.one, tm);
+        v[id] = en;
+    } else if constexpr (kFma == 7) {
+        // e' on the FMA pipe, a' one IADD3: 11 ALU-pipe instructions.
+        const uint32_t dx = mad32(mad32(v[ih], k.one, kw), k.one, v[id]);
+        const uint32_t md = mad32(v[id], k.neg, f_maj(v[ia], v[ib], v[ic]));
+        const uint32_t cx = mad32(f_ch(v[ie], v[jf], v[ig]), k.one, dx);
+        const uint32_t en = mad32(big_sigma1(v[ie]), k.one, cx);
         v[ih] = add3(md, big_sigma0(v[ia]), en);
         v[id] = en;
     } else {

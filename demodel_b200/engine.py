@@ -113,6 +113,30 @@ class Engine:
               "dm_stream_resume")
         return sid.value
 
+    def stream_suspend(self, sid: int) -> int:
+        """Save an interrupted download under <cas_dir>/partial and close the stream; returns the byte count
+        saved (the proxy re-requests `Range: bytes=<that>-`)."""
+        off = C.c_uint64()
+        check(self._lib.dm_stream_suspend(self._h, sid, C.byref(off)), "dm_stream_suspend")
+        return off.value
+
+    def stream_resume_saved(self, expect: bytes, size_hint: int = 0) -> Optional[tuple[int, int]]:
+        """(stream id, resume offset) continuing a download saved by stream_suspend - also after a restart of the
+        engine over the same cas_dir - or None when nothing is saved for this digest."""
+        sid, off = C.c_uint64(), C.c_uint64()
+        rc = self._lib.dm_stream_resume_saved(self._h, _digest_arg(expect), size_hint, C.byref(sid), C.byref(off))
+        if rc == DM_ENOENT:
+            return None
+        check(rc, "dm_stream_resume_saved")
+        return sid.value, off.value
+
+    def error_detail(self, ident: int = 0) -> str:
+        """Detail text of the last failing call on stream / reader `ident` (0 = calls without an id)."""
+        n = C.c_size_t()
+        buf = C.create_string_buffer(1024)
+        check(self._lib.dm_error_detail(self._h, ident, buf, 1024, C.byref(n)), "dm_error_detail")
+        return buf.value.decode(errors="replace")
+
     def stream_set_meta(self, sid: int, key: str, value: str) -> None:
         check(self._lib.dm_stream_set_meta(self._h, sid, key.encode(), value.encode()), "dm_stream_set_meta")
 
@@ -207,6 +231,47 @@ class Engine:
             return False
         check(rc, "dm_cache_evict")
         return True
+
+    # -- URL-keyed requests (the OnRequest hook is handed a URL) -----------------------
+    def alias_put(self, key: str, digest: bytes) -> None:
+        check(self._lib.dm_cache_alias_put(self._h, key.encode(), _digest_arg(digest)), "dm_cache_alias_put")
+
+    def alias_get(self, key: str) -> Optional[bytes]:
+        out = (C.c_uint8 * 32)()
+        rc = self._lib.dm_cache_alias_get(self._h, key.encode(), out)
+        if rc == DM_ENOENT:
+            return None
+        check(rc, "dm_cache_alias_get")
+        return bytes(out)
+
+    def proxy_fetch(self, url: str, body, expect: Optional[bytes] = None, chunk: int = 32768) -> tuple[bytes, bool]:
+        """OnResponse twin for one body fetched under `url` (BodyTee + SetURL): (digest, matched)."""
+        ptr, n = _buf_ptr(body)
+        out = (C.c_uint8 * 32)()
+        matched = C.c_int()
+        check(self._lib.dm_proxy_fetch(self._h, url.encode(), ptr, n, _digest_arg(expect), chunk, out, C.byref(matched)),
+              "dm_proxy_fetch")
+        return bytes(out), bool(matched.value)
+
+    def proxy_request(self, url: str) -> Optional[tuple[int, int]]:
+        """OnRequest twin: (reader, size) when the URL names a cached blob (digest in the URL, or alias), else None."""
+        rid, size = C.c_uint64(), C.c_uint64()
+        rc = self._lib.dm_proxy_request(self._h, url.encode(), C.byref(rid), C.byref(size))
+        if rc == DM_ENOENT:
+            return None
+        check(rc, "dm_proxy_request")
+        return rid.value, size.value
+
+    def proxy_manifest(self, body: bytes, content_encoding: Optional[str] = None, chunk: int = 32768, max_layers: int = 64):
+        """OnResponse twin for a manifest response: passes the body through, inflates gzip, parses, prefetches.
+        Returns [(digest, size, media_type, stream_id)]."""
+        layers = (_lib.DmLayer * max_layers)()
+        ids = (C.c_uint64 * max_layers)()
+        n = C.c_uint32()
+        ptr, nbytes = _buf_ptr(body)
+        check(self._lib.dm_proxy_manifest(self._h, ptr, nbytes, content_encoding.encode() if content_encoding else None,
+                                          chunk, layers, ids, max_layers, C.byref(n)), "dm_proxy_manifest")
+        return [(bytes(layers[i].digest), layers[i].size, layers[i].media_type.decode(), ids[i]) for i in range(min(n.value, max_layers))]
 
     def fetch(self, digest: bytes, chunk: int = 1 << 20) -> Optional[bytes]:
         """Whole cached blob, read the way the hit path would stream it."""
@@ -312,6 +377,14 @@ def synth_fill_host(seed: int, blob: int, byte_off: int, nbytes: int) -> np.ndar
     out = np.empty(nbytes, dtype=np.uint8)
     _lib.load().dm_synth_fill_host(seed, blob, byte_off, C.c_void_p(out.ctypes.data), nbytes)
     return out
+
+
+def gunzip(data: bytes, cap: int = 1 << 22) -> bytes:
+    """dm_gunzip: inflate a gzip / zlib body (manifests served with Content-Encoding: gzip)."""
+    out = C.create_string_buffer(max(cap, 1))
+    n = C.c_size_t()
+    check(_lib.load().dm_gunzip(data, len(data), out, cap, C.byref(n)), "dm_gunzip")
+    return out.raw[:n.value]
 
 
 def shard_of(digest: bytes, n_shards: int) -> int:

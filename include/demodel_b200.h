@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 1u
+#define DM_ABI_VERSION 2u   /* 2: dm_error_detail, URL aliases, saved checkpoints, dm_gunzip, DM_F_NUMA_LOCAL; dm_stats grew */
 
 typedef enum dm_err {
     DM_OK        = 0,
@@ -58,6 +58,8 @@ typedef struct dm_engine dm_engine;   /* opaque; owned by caller between create/
                                   * nothing is retained or published (also what a blob whose size_hint
                                   * exceeds hbm_cas_bytes gets automatically) */
 #define DM_F_DISK_SYNC    0x2u  /* dm_stream_finish returns only after the disk tier holds the blob */
+#define DM_F_NUMA_LOCAL   0x4u  /* pin the ring / bounce buffers and start the engine's threads on the NUMA node the
+                                  * GPU hangs off (sysfs); silently skipped when the topology is not visible */
 
 typedef struct dm_config {
     uint32_t struct_size;     /* = sizeof(dm_config); ABI guard */
@@ -92,6 +94,9 @@ typedef struct dm_stats {
     uint64_t ring_slabs_free;
     uint64_t open_readers;
     uint64_t free_stream_slots;   /* == max_streams when no stream is open or draining */
+    int64_t  numa_node;           /* DM_F_NUMA_LOCAL: the node the engine bound itself to; -1 = not bound */
+    uint64_t aliases;             /* URL / ETag -> digest entries (dm_cache_alias_put) */
+    uint64_t suspended;           /* interrupted downloads saved under <cas_dir>/partial (dm_stream_suspend) */
 } dm_stats;
 
 /* ---- engine lifetime (start.go:167-216) -------------------------------- */
@@ -102,6 +107,12 @@ void        dm_engine_destroy(dm_engine *e);
 int         dm_engine_stats(dm_engine *e, dm_stats *out);
 const char *dm_strerror(int err);
 const char *dm_last_error(void);                         /* thread-local detail text */
+/* Detail text of the last failing call on stream / reader `id` (0: calls that take no id, such as
+ * dm_stream_open, dm_cache_open, dm_ingest_device), retrievable from ANY thread - what a cgo caller
+ * uses instead of dm_last_error(): a goroutine can change OS threads between the call that failed and
+ * the one that asks why.  e == NULL: the last dm_engine_create failure in this process.  *len receives
+ * the full length; up to cap-1 bytes + NUL are copied.  The engine remembers the last 4096 ids. */
+int         dm_error_detail(dm_engine *e, uint64_t id, char *buf, size_t cap, size_t *len);
 
 /* Kernel shape the engine picks for `n_resident` co-resident streams: streams per
  * warp, 1 = warp-per-stream (deep), 2..16 = group, 32 = lane-per-stream (wide).  Pure function. */
@@ -141,6 +152,18 @@ typedef struct dm_checkpoint {
 int dm_stream_checkpoint(dm_engine *e, uint64_t id, dm_checkpoint *out);
 int dm_stream_resume(dm_engine *e, const dm_checkpoint *ck, const uint8_t expect[32], uint64_t size_hint, uint64_t *id);
 
+/* Interrupted downloads that survive a proxy restart (needs cas_dir).
+ * dm_stream_suspend closes a stream opened WITH an expected digest and saves what it has: the SHA-256
+ * mid-state after the last whole block received in order, and those bytes, under
+ * <cas_dir>/partial/<hex>.ckpt / <hex>.part.  *resume_from = the byte count saved (multiple of 64): the
+ * proxy re-requests upstream with `Range: bytes=<resume_from>-`.  The id is released.
+ * dm_stream_resume_saved - in this process or after dm_engine_create over the same cas_dir - opens a stream
+ * that continues from the saved state: the saved prefix is loaded back into the blob's HBM extent (so the
+ * finished blob is cached whole) and only the bytes from *resume_from on are hashed.  DM_ENOENT when
+ * nothing is saved for `expect`.  The saved files are removed once a resumed stream has taken them over. */
+int dm_stream_suspend(dm_engine *e, uint64_t id, uint64_t *resume_from);
+int dm_stream_resume_saved(dm_engine *e, const uint8_t expect[32], uint64_t size_hint, uint64_t *id, uint64_t *resume_from);
+
 /* Response headers worth replaying on a hit (Content-Type, ETag, Last-Modified,
  * the request URL ...).  Stored with the blob — in the `.meta` sidecar on the
  * disk tier — and returned by dm_cache_meta.  At most 64 entries per stream. */
@@ -148,7 +171,12 @@ int dm_stream_set_meta(dm_engine *e, uint64_t id, const char *key, const char *v
 
 /* Zero-copy variant: borrow a window of the pinned ring, Read() into it,
  * then commit the bytes actually read.  At most one outstanding window per
- * stream; *cap >= 1 on success. */
+ * stream; *cap >= 1 on success.
+ * Lifetime: [ptr, ptr+cap) belongs to the caller from dm_stream_acquire until
+ * dm_stream_commit RETURNS.  After the commit the engine may DMA the slab and
+ * hand it to another stream at any moment, so anything else that reads the
+ * window (the client-side write of the same bytes) must finish BEFORE the
+ * commit: acquire, Read, Write to the client, commit. */
 int dm_stream_acquire(dm_engine *e, uint64_t id, void **ptr, size_t *cap);
 int dm_stream_commit(dm_engine *e, uint64_t id, size_t len);
 /* Optional, non-blocking: upstream hit EOF, no more bytes will be written.
@@ -184,6 +212,17 @@ int dm_cache_evict(dm_engine *e, const uint8_t digest[32]);   /* HBM tier only; 
  * verification, reads fail with DM_ESTATE.  DM_ENOENT: nothing in flight.
  * *size_hint = the Content-Length the ingesting stream was opened with (0 = unknown). */
 int dm_cache_follow(dm_engine *e, const uint8_t digest[32], uint64_t *reader, uint64_t *size_hint);
+
+/* URL -> digest index for the OnRequest hit check (start.go:197-200 hands the hook a request, not a
+ * digest).  OCI blob URLs carry `sha256:<hex>`; HuggingFace `resolve/<rev>/<file>` URLs (the first clients
+ * /root/reference/README.md:16-21 lists) do not.  The tee records URL (or ETag / LFS oid string) -> digest
+ * when a body verifies; a later request for the same key is answered from the CAS.  `key` is any
+ * NUL-terminated string up to 4096 bytes.  With cas_dir the index is an append-only log
+ * (<cas_dir>/aliases.log) replayed by dm_engine_create; a put for an existing key replaces it.
+ * dm_cache_alias_get: DM_ENOENT when the key is unknown (the digest may since have been evicted from both
+ * tiers: dm_cache_open decides). */
+int dm_cache_alias_put(dm_engine *e, const char *key, const uint8_t digest[32]);
+int dm_cache_alias_get(dm_engine *e, const char *key, uint8_t digest_out[32]);
 
 /* ---- device-resident ingest -------------------------------------------- */
 /* Hash-and-cache n blobs whose bytes are ALREADY in this GPU's HBM (landed
@@ -228,6 +267,12 @@ int dm_manifest_parse(const char *json, size_t len, dm_layer *out, uint32_t max_
  * expected digest and size (so its extent is reserved and the body is verified
  * as it arrives).  ids[i] = 0 for layers that are cache hits or duplicates. */
 int dm_manifest_prefetch(dm_engine *e, const dm_layer *layers, uint32_t n, uint64_t *ids);
+/* Registries answer manifest requests with `Content-Encoding: gzip` when the client allows it - the one
+ * cached body the reference documents is such a response (CONTRIBUTING.md:76-99,116).  Inflates a gzip
+ * (RFC 1952) or raw-deflate-in-zlib (RFC 1950) body of `len` bytes into dst[cap]; *out_len = inflated size.
+ * DM_EINVAL: malformed stream or CRC / length mismatch; DM_ENOMEM: cap too small (*out_len = needed size
+ * when the trailer states it).  Pure host code; manifests are a few KiB. */
+int dm_gunzip(const void *src, size_t len, void *dst, size_t cap, size_t *out_len);
 
 /* ---- synthetic blob bytes ------------------------------ */
 /* Counter-based generator: byte j of blob `blob` under `seed` is a pure
@@ -260,6 +305,20 @@ int dm_proxy_drive(dm_engine *e, const void *host_base, const uint64_t *offsets,
  * pieces (the cache-hit path), `nthreads` readers. */
 int dm_proxy_serve(dm_engine *e, const uint8_t *digests, uint32_t n, void *host_base,
                    const uint64_t *offsets, size_t chunk, int nthreads, double *seconds);
+
+/* Single-connection twins of the two hooks for callers that work with URLs (demodel_b200/csrc/proxy_hooks.hpp:
+ * BodyTee::SetURL, HitReader(url), ManifestTee).
+ * dm_proxy_fetch: the OnResponse tee for one body fetched under `url`; expect may be NULL (HuggingFace resolve/
+ * URL: digest unknown until hashed).  A verified body is entered in the alias index under the URL.
+ * dm_proxy_request: the OnRequest check - a digest in the URL (OCI `sha256:<hex>`) or the alias index.
+ * DM_ENOENT = miss; DM_OK = *reader is an open cache reader over *size bytes.
+ * dm_proxy_manifest: the OnResponse tee for a manifest response, Content-Encoding "gzip" or identity (NULL):
+ * passes the body through, inflates, parses, prefetches.  Up to max_layers entries are returned. */
+int dm_proxy_fetch(dm_engine *e, const char *url, const void *body, uint64_t len, const uint8_t *expect,
+                   size_t chunk, uint8_t digest_out[32], int *matched_out);
+int dm_proxy_request(dm_engine *e, const char *url, uint64_t *reader, uint64_t *size);
+int dm_proxy_manifest(dm_engine *e, const void *body, uint64_t len, const char *content_encoding, size_t chunk,
+                      dm_layer *layers_out, uint64_t *ids_out, uint32_t max_layers, uint32_t *n_layers);
 
 #ifdef __cplusplus
 }

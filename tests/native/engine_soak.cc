@@ -28,7 +28,8 @@ extern "C" void dmo_sha256(const void *data, size_t len, uint8_t out[32]);
 static std::atomic<int> failures{0};
 static std::atomic<int> where[64];             // op each worker is in (watchdog report)
 static std::atomic<long> ops{0}, enomem{0}, followed{0};
-static uint64_t g_arena = 0;                   // a body larger than the arena is verified only: no out-of-order ranges
+static uint64_t g_arena = 0;
+static bool g_disk = false;                      // the engine has a disk tier (cas_dir): suspend / resume_saved are available                   // a body larger than the arena is verified only: no out-of-order ranges
 
 struct Body { std::vector<uint8_t> bytes; uint8_t digest[32]; };
 static std::vector<Body> bodies;
@@ -83,7 +84,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
         uint8_t got[32];
         int matched = -1, rc;
         uint64_t id = 0;
-        const int op = (int)(rng() % 15);
+        const int op = (int)(rng() % 20);
         ops++;
         where[tid & 63] = op * 1000 + (int)(n >> 10);
         if (op <= 1) {                                               // sequential, random piece size
@@ -354,6 +355,104 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
                 CHECK(dm_cache_close(e, rid) < 0);
                 CHECK(dm_cache_read(e, rid, 0, scratch.data(), 1, &nread) < 0);
             }
+        } else if (op == 15) {                                       // URL-keyed fetch (digest unknown up front) and hit by URL
+            char url[160];
+            snprintf(url, sizeof url, "https://huggingface.co/org/model/resolve/main/file-%zu-%d.safetensors", (size_t)(&b - &bodies[0]), (int)(rng() % 3));
+            rc = dm_proxy_fetch(e, url, p, n, (rng() & 1) ? b.digest : nullptr, 1 + rng() % 60000, got, &matched);
+            if (rc == DM_ENOMEM) { enomem++; continue; }
+            if (rc == DM_ECUDA && g_inject) { cuda_failed++; continue; }
+            CHECK(rc == DM_OK);
+            CHECK(matched == 1 && memcmp(got, b.digest, 32) == 0);
+            uint8_t ad[32];
+            CHECK(dm_cache_alias_get(e, url, ad) == DM_OK && memcmp(ad, b.digest, 32) == 0);
+            uint64_t rid = 0, size = 0;
+            rc = dm_proxy_request(e, url, &rid, &size);
+            if (rc == DM_OK) {                                       // (a miss is legal: verify-only engine, or evicted meanwhile)
+                CHECK(size == n);
+                size_t nread = 0;
+                if (n) {
+                    const size_t off = rng() % n;
+                    rc = dm_cache_read(e, rid, off, scratch.data(), std::min<size_t>(n - off, 50000), &nread);
+                    if (rc == DM_OK) CHECK(nread > 0 && memcmp(scratch.data(), p + off, nread) == 0);
+                    else CHECK(tolerate(rc));
+                }
+                CHECK(dm_cache_close(e, rid) == DM_OK);
+            } else CHECK(rc == DM_ENOENT);
+            // an OCI URL names its digest: resolved without the index
+            char oci[200] = "https://registry.ollama.ai/v2/library/x/blobs/sha256:";
+            for (int i = 0; i < 32; ++i) snprintf(oci + strlen(oci), 3, "%02x", b.digest[i]);
+            rc = dm_proxy_request(e, oci, &rid, &size);
+            if (rc == DM_OK) { CHECK(size == n); CHECK(dm_cache_close(e, rid) == DM_OK); } else CHECK(rc == DM_ENOENT);
+            CHECK(dm_cache_alias_get(e, "https://never/seen", ad) == DM_ENOENT);
+            CHECK(dm_cache_alias_put(e, "bad\nkey", b.digest) == DM_EINVAL);
+        } else if (op == 16) {                                       // interrupted download saved to the disk tier and picked up again
+            // a body private to this thread: the saved files are named by the expected digest
+            std::vector<uint8_t> mine(70000 + rng() % 400000);
+            dm_synth_fill_host(0xDE40DE1, 70000 + (uint64_t)tid * 1000 + rng() % 8, 0, mine.data(), mine.size());
+            uint8_t md[32];
+            dmo_sha256(mine.data(), mine.size(), md);
+            const size_t mn = mine.size(), cut = 1 + rng() % (mn - 1);
+            rc = dm_stream_open(e, md, mn, &id);
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
+            rc = dm_stream_write(e, id, mine.data(), cut);
+            if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); continue; }
+            uint64_t from = ~0ull;
+            rc = dm_stream_suspend(e, id, &from);
+            if (!g_disk || vo || mn > g_arena) { CHECK(rc == DM_ESTATE); CHECK(dm_stream_abort(e, id) == DM_OK); continue; }
+            if (rc != DM_OK) { CHECK(tolerate(rc) || rc == DM_EIO); dm_stream_abort(e, id); continue; }
+            CHECK(from <= cut && from % 64 == 0 && from == cut / 64 * 64);
+            CHECK(dm_stream_write(e, id, mine.data(), 1) < 0);       // suspend released the id
+            uint64_t from2 = ~0ull;
+            rc = dm_stream_resume_saved(e, md, mn, &id, &from2);
+            if (rc != DM_OK) { CHECK(tolerate(rc)); continue; }       // (arena full while re-loading the prefix)
+            CHECK(from2 == from);
+            rc = dm_stream_write(e, id, mine.data() + from, mn - from);
+            if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); continue; }
+            rc = finish_or_skip(e, id, false, got, &matched);
+            if (rc == 1) continue;
+            CHECK(rc == DM_OK);
+            CHECK(matched == 1 && memcmp(got, md, 32) == 0);
+            uint64_t rid = 0, size = 0;
+            if (dm_cache_open(e, md, &rid, &size) == DM_OK) {        // cached WHOLE: the saved prefix came back from disk
+                CHECK(size == mn);
+                size_t nread = 0;
+                rc = dm_cache_read(e, rid, 0, scratch.data(), std::min<size_t>(mn, scratch.size()), &nread);
+                if (rc == DM_OK) CHECK(nread == std::min<size_t>(mn, scratch.size()) && memcmp(scratch.data(), mine.data(), nread) == 0);
+                else CHECK(tolerate(rc));
+                CHECK(dm_cache_close(e, rid) == DM_OK);
+                dm_cache_evict(e, md);
+            }
+            CHECK(dm_stream_resume_saved(e, md, mn, &id, &from2) == DM_ENOENT);      // the saved files were consumed
+        } else if (op == 17) {                                       // error text by id, from another thread (cgo: goroutines migrate)
+            const uint64_t bogus = 0x7100000000ull + (uint64_t)tid * 4096 + rng() % 1000;
+            CHECK(dm_stream_write(e, bogus, scratch.data(), 1) == DM_EINVAL);
+            const std::string here = dm_last_error();
+            std::string there;
+            std::thread([&] { char t[256]; size_t l = 0; if (dm_error_detail(e, bogus, t, sizeof t, &l) == DM_OK) there.assign(t, std::min(l, sizeof t - 1)); }).join();
+            CHECK(!here.empty() && here == there);
+            char tiny[4];
+            size_t full = 0;
+            CHECK(dm_error_detail(e, bogus, tiny, sizeof tiny, &full) == DM_OK && full == here.size() && strlen(tiny) == 3);
+        } else if (op == 18 || op == 19) {                           // finish racing abort (18) / a second finish (19) on one id
+            rc = dm_stream_open(e, b.digest, n, &id);
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
+            rc = dm_stream_write(e, id, p, n);
+            if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); continue; }
+            int rc2 = 0, m2 = -1;
+            uint8_t got2[32];
+            std::thread other([&] {
+                if (rng() & 1) std::this_thread::yield();
+                rc2 = op == 18 ? dm_stream_abort(e, id) : dm_stream_finish(e, id, got2, &m2);
+            });
+            rc = dm_stream_finish(e, id, got, &matched);
+            other.join();
+            // whoever loses sees a closed / unknown stream; nobody hangs, nothing leaks (checked at the end of the soak)
+            if (rc == DM_OK) CHECK(matched == 1 && memcmp(got, b.digest, 32) == 0);
+            else { CHECK(rc == DM_ESTATE || rc == DM_EINVAL || tolerate(rc)); if (rc == DM_ENOMEM || rc == DM_ECUDA) dm_stream_abort(e, id); }
+            if (op == 19 && rc2 == DM_OK) CHECK(m2 == 1 && memcmp(got2, b.digest, 32) == 0);
+            if (rc2 != DM_OK) CHECK(rc2 == DM_ESTATE || rc2 == DM_EINVAL || tolerate(rc2));
         } else if (op == 11) {                                       // metadata + stats are always safe to call
             dm_stats st;
             CHECK(dm_engine_stats(e, &st) == DM_OK);
@@ -514,7 +613,8 @@ int main(int argc, char **argv)
     cfg.slab_bytes = (uint32_t)env_u64("RIG_SLAB", 64u << 10);
     cfg.max_streams = 256;
     cfg.cas_dir = cas_dir;
-    cfg.flags = verify_only ? DM_F_NO_HBM_CAS : 0;
+    g_disk = cas_dir != nullptr;
+    cfg.flags = (verify_only ? DM_F_NO_HBM_CAS : 0) | DM_F_NUMA_LOCAL;          // (no PCI topology on the rig: the flag is a no-op)
     dm_engine *e = nullptr;
     if (dm_engine_create(&cfg, &e) != DM_OK) { fprintf(stderr, "create failed: %s\n", dm_last_error()); return 1; }
     std::vector<std::thread> th;

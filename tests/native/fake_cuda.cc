@@ -119,6 +119,7 @@ cudaError_t cudaDeviceSynchronize(void)
     for (fakeStream *s : all) s->drain();
     return cudaSuccess;
 }
+cudaError_t cudaDeviceGetPCIBusId(char *buf, int len, int) { if (len > 0) buf[0] = 0; return cudaErrorInvalidValue; }   // no PCI topology on the rig
 cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = 1ull << 30; return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t) { return "fake cuda error"; }
 // The real runtime keeps a per-thread "last error" that cudaGetLastError returns and clears - and a query that says

@@ -21,6 +21,7 @@ extern "C" {
 cudaError_t cudaGetDeviceCount(int *n);
 cudaError_t cudaSetDevice(int dev);
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int dev);
+cudaError_t cudaDeviceGetPCIBusId(char *buf, int len, int dev);
 cudaError_t cudaDeviceSynchronize(void);
 cudaError_t cudaMemGetInfo(size_t *free_b, size_t *total_b);
 const char *cudaGetErrorString(cudaError_t e);

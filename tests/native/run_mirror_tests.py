@@ -26,6 +26,7 @@ import demodel_b200  # noqa: E402
 from tests import _oracle  # noqa: E402
 import tests.test_gpu_parity as T  # noqa: E402
 import tests.test_manifest as TM  # noqa: E402
+import tests.test_gpu_hooks as TH  # noqa: E402
 
 import tempfile  # noqa: E402
 
@@ -44,7 +45,7 @@ def main():
         marks += mm if isinstance(mm, list) else [mm]
         return any(m.name == "gpu" for m in marks)
 
-    cases = [(name, fn) for mod in (T, TM) for name, fn in sorted(vars(mod).items())
+    cases = [(name, fn) for mod in (T, TM, TH) for name, fn in sorted(vars(mod).items())
              if name.startswith("test_") and callable(fn) and is_gpu(mod, fn)]
     for name, fn in cases:
         if name in ("test_baseline_sized_properties", "test_ollama_pull_at_the_fixture_sizes"):

@@ -85,6 +85,9 @@ int main()
     bad += check<0>("kFma 0 (ptxas ordering)");
     bad += check<1>("kFma 1 (IMAD additions)");
     bad += check<4>("kFma 4 (short chain)");
+    bad += check<5>("kFma 5 (short chain, all IMAD)");
+    bad += check<6>("kFma 6 (e' IADD3, a' IMAD)");
+    bad += check<7>("kFma 7 (e' IMAD, a' IADD3)");
     if (bad) { printf("ROUND FORMS FAILED\n"); return 1; }
     printf("ROUND FORMS OK\n");
     return 0;

@@ -33,9 +33,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_layout():
     lib = demodel_b200.load()
-    assert lib.dm_abi_version() == 1
+    assert lib.dm_abi_version() == 2
     assert C.sizeof(_lib.DmConfig) == 48        # matches the C layout on LP64
-    assert C.sizeof(_lib.DmStats) == 20 * 8
+    assert C.sizeof(_lib.DmStats) == 23 * 8
 
 
 def test_strerror_covers_all_codes():

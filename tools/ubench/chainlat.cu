@@ -47,6 +47,38 @@ __global__ void probe(unsigned long long *cycles, unsigned *sink, int iters, uns
                 unsigned x;
                 asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(x) : "r"(r), "r"(s), "r"(t));
                 asm("{ .reg .u32 q; add.u32 q, %1, %2; add.u32 %0, q, %3; }" : "=r"(a) : "r"(x), "r"(b), "r"(c));
+            } else if (MODE == 9) asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(a) : "r"(a), "r"(b), "r"(c));          // LOP3 -> LOP3
+            else if (MODE == 10) asm("{ .reg .u32 q; add.u32 q, %1, %2; add.u32 %0, q, %3; }" : "=r"(a) : "r"(a), "r"(b), "r"(c));   // IADD3 -> IADD3
+            else if (MODE == 11) {                                                                 // SHF -> LOP3 (per pair)
+                a = __funnelshift_r(a, a, 7);
+                asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(a) : "r"(a), "r"(b), "r"(c));
+            } else if (MODE == 12) {                                                               // SHF -> IADD3 (per pair)
+                a = __funnelshift_r(a, a, 7);
+                asm("{ .reg .u32 q; add.u32 q, %1, %2; add.u32 %0, q, %3; }" : "=r"(a) : "r"(a), "r"(b), "r"(c));
+            } else if (MODE == 13) {                                                               // LOP3 -> IADD3 (per pair)
+                asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(a) : "r"(a), "r"(b), "r"(c));
+                asm("{ .reg .u32 q; add.u32 q, %1, %2; add.u32 %0, q, %3; }" : "=r"(a) : "r"(a), "r"(b), "r"(d));
+            } else if (MODE == 14) {                                                               // 3 SHF -> LOP3 (per step)
+                const unsigned r = __funnelshift_r(a, a, 6), s = __funnelshift_r(a, a, 11), t = __funnelshift_r(a, a, 25);
+                asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(a) : "r"(r), "r"(s), "r"(t));
+            } else if (MODE == 15) {                                                               // 3 SHF -> LOP3 -> IMAD (per step)
+                const unsigned r = __funnelshift_r(a, a, 6), s = __funnelshift_r(a, a, 11), t = __funnelshift_r(a, a, 25);
+                unsigned x;
+                asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(x) : "r"(r), "r"(s), "r"(t));
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(x), "r"(one), "r"(b));
+            } else if (MODE == 16) {                                                               // LOP3 -> IMAD (per pair)
+                asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(a) : "r"(a), "r"(b), "r"(c));
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(a), "r"(one), "r"(d));
+            } else if (MODE == 17) {                                                               // ALU x2 + IMAD x2 interleaved, IMADs cross-dependent
+                a = __funnelshift_r(a, a, 7);
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(b) : "r"(b), "r"(one), "r"(d));
+                c = __funnelshift_r(c, c, 9);
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(d), "r"(one), "r"(b));
+            } else if (MODE == 18) {                                                               // 4 independent chains, alternating pipes
+                a = __funnelshift_r(a, a, 7);
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(b) : "r"(b), "r"(one), "r"(p19));
+                c = __funnelshift_r(c, c, 9);
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(d), "r"(one), "r"(p19));
             }
         }
     }
@@ -78,5 +110,15 @@ int main()
     run<6>("4 x IMAD.WIDE (+ 4 LOP3)", 4, cyc, sink);
     run<7>("4 x IMAD.HI (+ 4 IADD)", 4, cyc, sink);
     run<8>("3 SHF -> LOP3 -> IADD3 (short chain step)", 1, cyc, sink);
+    run<9>("LOP3 -> LOP3 (dependent)", 1, cyc, sink);
+    run<10>("IADD3 -> IADD3 (dependent)", 1, cyc, sink);
+    run<11>("SHF -> LOP3 (per pair)", 1, cyc, sink);
+    run<12>("SHF -> IADD3 (per pair)", 1, cyc, sink);
+    run<13>("LOP3 -> IADD3 (per pair)", 1, cyc, sink);
+    run<14>("3 SHF -> LOP3 (per step)", 1, cyc, sink);
+    run<15>("3 SHF -> LOP3 -> IMAD (per step)", 1, cyc, sink);
+    run<16>("LOP3 -> IMAD (per pair)", 1, cyc, sink);
+    run<17>("SHF, IMAD, SHF, IMAD (IMADs cross-dependent)", 4, cyc, sink);
+    run<18>("SHF, IMAD, SHF, IMAD (4 independent chains)", 4, cyc, sink);
     return cudaDeviceSynchronize() == cudaSuccess ? 0 : 1;
 }
