@@ -92,12 +92,13 @@ def _int_issue_roofline(n_streams, hashed_gbs, sm_mhz):
     """The bound that actually binds SHA-256 on sm_100a (profiles/r01_ubench_issue_rates.txt):
     the ALU pipe takes one warp-instruction per 2 cycles per sub-partition.  Chip ceiling: >= 1040 ALU-pipe
     instructions per 64-byte block per warp of 32 lanes on 592 sub-partitions.  Few streams: one warp per
-    stream needs >= 12 ALU-pipe instructions = 24 cycles per round, 64 rounds per 64 bytes.  Reported beside the
-    HBM roofline the metric asks for; never raises."""
+    stream needs the round's six rotations and four boolean functions on that pipe whatever is done with the
+    additions = 20 cycles per round, 64 rounds per 64 bytes (the shipped round form issues 11: 22 cycles).
+    Reported beside the HBM roofline the metric asks for; never raises."""
     try:
         ghz = (sm_mhz or 1965.0) / 1e3
         chip = 592 * ghz * (32 * 64) / (1040 * 2)                 # GB/s
-        per_stream = ghz / 24.0                                    # GB/s: 1 byte per round
+        per_stream = ghz / 20.0                                    # GB/s: 1 byte per round
         peak = min(chip, n_streams * per_stream)
         return {"bound": "int32 ALU-pipe issue", "peak": peak, "achieved": hashed_gbs, "frac": hashed_gbs / peak, "unit": "GB/s hashed",
                 "chip_ceiling": chip, "per_stream_ceiling": per_stream, "streams": n_streams, "sm_ghz": ghz}
@@ -314,6 +315,7 @@ def main():
     ap.add_argument("--e2e-threads", type=int, default=0)
     ap.add_argument("--numa-bind", action="store_true", help="pin the process to the GPU's NUMA node (default when N > 1)")
     ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--cas-slack-mib", type=int, default=4096, help="HBM arena beyond one copy of the workload (ring-path bodies, probes)")
     ap.add_argument("--blobs", type=int, default=0, help="override: number of blobs (with --blob-bytes)")
     ap.add_argument("--blob-bytes", type=int, default=0)
     args = ap.parse_args()
@@ -370,8 +372,9 @@ def main():
     total = sum(sizes)
     job_total = sum(sizes_all) if routing == "digest" else total * world      # bytes the whole job moves per step
 
-    cas_bytes = 0 if args.hash_only else (span + (64 << 20) if world == 1 else int(1.5 * span) + (64 << 20))   # N > 1: room for the
-    eng = demodel_b200.Engine(                                                                          # digest-routed probe's uneven sharesdevice=local, hbm_cas_bytes=max(cas_bytes, 256 << 20) + (4 << 30), ring_bytes=args.ring_mib << 20,
+    # one copy of the workload (N > 1: 1.5 copies, room for the digest-routed probe's uneven shares) + slack for ring-path bodies
+    cas_bytes = 0 if args.hash_only else (span + (64 << 20) if world == 1 else int(1.5 * span) + (64 << 20))
+    eng = demodel_b200.Engine(device=local, hbm_cas_bytes=max(cas_bytes, 256 << 20) + (args.cas_slack_mib << 20), ring_bytes=args.ring_mib << 20,
                               slab_bytes=args.slab_kib << 10, max_streams=max(65536, n + 1024))
     dev = torch.empty(max(span, 16), dtype=torch.uint8, device=f"cuda:{local}")
     # blob indices are consecutive per rank only when world == 1; fill one by one otherwise
@@ -662,13 +665,18 @@ def main():
         del src, cache
 
     if rank == 0:
-        traffic = None
+        # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from an
+        # ncu capture of this workload (tools/prof_default.sh writes profiles/roofline_traffic.json).  It is only
+        # reported when the capture was taken with the kernel variant that ran here.
+        traffic, traffic_src = None, None
+        lib_ = demodel_b200.load()
+        variant_now = os.environ.get("DM_KERNEL_VARIANT") or f"{lib_.dm_default_kernel_variant(0)},{lib_.dm_default_kernel_variant(1)}"
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and not (args.hash_only or args.kernel):
             try:
-                traffic = json.load(open(tpath)).get(args.workload)
-                if args.hash_only or args.kernel:
-                    traffic = None          # the capture is of the default mode only
+                ent = json.load(open(tpath)).get(args.workload)
+                if isinstance(ent, dict) and ent.get("kernel_variant") == variant_now:
+                    traffic, traffic_src = ent["bytes"], ent.get("source")
             except Exception:
                 traffic = None
         line = {
@@ -684,7 +692,7 @@ def main():
                                        else f"shard{world} (URL-hash homed, no collective)"),
                        "blobs_per_rank": shard_counts, "scaled": wl.get("scaled"), "job_bytes_per_step": job_total},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel_variant": variant_now, "peak_source": peak_src,
                          "algorithmic_bytes_per_blob_byte": bytes_per_blob_byte, "kernel_ms_per_step": kernel_ms_max / args.steps,
                          "int_issue": _int_issue_roofline(n, achieved / bytes_per_blob_byte, (clocks or {}).get("sm_mhz"))},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "probes": probes,

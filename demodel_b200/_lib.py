@@ -63,6 +63,8 @@ class DmStats(C.Structure):
         ("numa_node", C.c_int64),
         ("aliases", C.c_uint64),
         ("suspended", C.c_uint64),
+        ("packed_bodies", C.c_uint64),
+        ("packs", C.c_uint64),
     ]
 
 
@@ -89,6 +91,7 @@ SIGNATURES = {
     "dm_error_detail": (C.c_int, [_P, C.c_uint64, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dm_shard_of": (C.c_uint32, [_P, C.c_uint32]),
     "dm_streams_per_warp": (C.c_uint32, [C.c_uint32]),
+    "dm_default_kernel_variant": (C.c_uint32, [C.c_int]),
     "dm_stream_open": (C.c_int, [_P, _P, C.c_uint64, _U64P]),
     "dm_stream_write": (C.c_int, [_P, C.c_uint64, _P, C.c_size_t]),
     "dm_stream_write_at": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, C.c_size_t]),

@@ -107,6 +107,8 @@ int dm_device_count(void)
     return n;
 }
 
+uint32_t dm_default_kernel_variant(int which) { return (uint32_t)(which ? dm::kDefaultDeepVariant : dm::kDefaultWideVariant); }
+
 uint32_t dm_streams_per_warp(uint32_t n_resident) { return (uint32_t)dm::streams_per_warp_for(n_resident); }
 
 uint32_t dm_shard_of(const uint8_t digest[32], uint32_t n_shards)
@@ -158,6 +160,7 @@ void dm_engine_destroy(dm_engine *e)
     if (e->ckpt_pinned) cudaFreeHost(e->ckpt_pinned);
     if (e->ing_ev0) cudaEventDestroy(e->ing_ev0);
     if (e->ing_ev1) cudaEventDestroy(e->ing_ev1);
+    if (e->pack_dev_base) cudaFree(e->pack_dev_base);
     if (e->d_states) cudaFree(e->d_states);
     if (e->h_digests) cudaFreeHost(e->h_digests);
     if (e->ring) cudaFreeHost(e->ring);
@@ -263,6 +266,11 @@ static int engine_create(const dm_config *cfg, dm_engine **out)
         e->slab_free.push_back(&e->slab_store[i]);
     }
 
+    if (!(e->cfg.flags & DM_F_NO_HBM_CAS) && e->cfg.slab_bytes >= 1024) {      // staging for tiny-body packs
+        e->tiny_max = std::min<uint32_t>(kTinyMax, e->cfg.slab_bytes / 4);
+        CU_INIT(cudaMalloc(&e->pack_dev_base, (uint64_t)kPackDevBufs * e->cfg.slab_bytes));
+        for (int i = 0; i < kPackDevBufs; ++i) e->pack_dev_free.push_back(e->pack_dev_base + (uint64_t)i * e->cfg.slab_bytes);
+    }
     CU_INIT(cudaMalloc(&e->d_states, 32ull * e->cfg.max_streams));
     CU_INIT(cudaHostAlloc(&e->h_digests, 32ull * e->cfg.max_streams, cudaHostAllocMapped));
     CU_INIT(cudaHostGetDevicePointer((void **)&e->d_digests, e->h_digests, 0));
@@ -326,6 +334,7 @@ int dm_engine_stats(dm_engine *e, dm_stats *o)
     o->numa_node = e->numa_node;
     { std::lock_guard<std::mutex> g(e->alias_mu); o->aliases = e->aliases.size(); }
     o->suspended = e->n_suspended;
+    o->packed_bodies = e->st_packed; o->packs = e->st_packs;
     return DM_OK;
 }
 
@@ -370,6 +379,10 @@ static int stream_open_impl(dm_engine *e, const uint8_t expect[32], uint64_t siz
         sp->capacity = x.len;
     }
     sp->size_hint = size_hint;
+    if (size_hint && size_hint <= e->tiny_max && !sp->verify_only) {       // announced tiny: no ring slab (see Stream::small)
+        sp->small.reset(new uint8_t[size_hint]);
+        sp->small_cap = (uint32_t)size_hint;
+    }
     {
         const int k = (int)(sp->id % kStripes);
         std::lock_guard<std::mutex> g(e->stripe_mu[k]);
@@ -402,6 +415,11 @@ static int stream_write_impl(dm_engine *e, uint64_t id, const void *buf, size_t 
     if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open for write");
     const uint8_t *p = static_cast<const uint8_t *>(buf);
     const uint32_t slab_bytes = e->cfg.slab_bytes;
+    if (s->small_cap && !s->cur && s->small_fill + len <= s->small_cap) {     // announced-tiny body: private buffer, no slab
+        if (len) memcpy(s->small.get() + s->small_fill, p, len);
+        s->small_fill += (uint32_t)len; s->received += len;
+        return DM_OK;
+    }
     while (len) {
         if (s->lost != DM_OK) return fail(s->lost, kLostText);
         if (!s->cur) {
@@ -432,6 +450,10 @@ static int stream_write_at_impl(dm_engine *e, uint64_t id, uint64_t offset, cons
     std::unique_lock<std::mutex> g(s->mu);
     if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open for write");
     if (s->lost != DM_OK) return fail(s->lost, kLostText);
+    if (s->small_cap && !s->cur) {                       // range parts need real slabs: move the private buffer's bytes into one
+        int rc = take_slab(e, s, g);
+        if (rc != DM_OK) return rc;
+    }
     if (offset < s->resume_base && offset + len > s->resume_base) {
         // A re-supplied prefix that runs across the resume point: the part below it is kept for caching
         // only (prefix_cover), the part above it is hashed.  Treat them as the two writes they are.
@@ -476,6 +498,7 @@ static int stream_write_at_impl(dm_engine *e, uint64_t id, uint64_t offset, cons
             if (!fresh) return fail(DM_ESTATE, "engine stopping");
             if (s->st != St::Open) { slab_put(e, fresh); return fail(DM_ESTATE, "stream closed while waiting for the ring"); }
             s->parts.push_back({offset, fresh, 0});
+            s->range_mode = true;
             continue;                                       // re-find (the vector may have changed while unlocked)
         }
         Stream::Part &pt = s->parts[idx];
@@ -501,6 +524,11 @@ static int stream_checkpoint_impl(dm_engine *e, uint64_t id, dm_checkpoint *out)
     if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open");
     if (s->cuda_failed) return fail(DM_ECUDA, "a CUDA copy or launch failed earlier on this stream: its state is not trusted");
     if (s->lost != DM_OK) return fail(s->lost, kLostText);
+    if (s->small_fill && !s->cur) {                      // bytes still in the private buffer of an announced-tiny body
+        int rc = take_slab(e, s, g);
+        if (rc != DM_OK) return rc;
+        if (s->st != St::Open) return fail(DM_ESTATE, "stream closed during checkpoint");
+    }
     if (!s->verify_only || (s->cur_fill & 63) == 0) {
         // push out what is staged so the checkpoint covers every whole block received in order
         // (a verify-only stream hashes slab by slab, so only a block-aligned partial slab may go early)
@@ -549,7 +577,7 @@ static int stream_resume_impl(dm_engine *e, const dm_checkpoint *ck, const uint8
     if (!sp) return fail(DM_ESTATE, "stream closed while resuming");
     Stream *s = sp.get();
     std::unique_lock<std::mutex> g(s->mu);
-    s->resume_base = s->dma_issued = s->hash_issued = ck->bytes;
+    s->resume_base = s->dma_issued = s->hash_issued = s->landed = ck->bytes;
     if (ck->bytes == 0 && s->has_expect && !s->verify_only) {
         std::lock_guard<std::mutex> g2(e->mu);
         auto &slot = e->inflight[s->expect];
@@ -690,9 +718,12 @@ static int stream_resume_saved_impl(dm_engine *e, const uint8_t expect[32], uint
     int rc = stream_resume_impl(e, &ck, expect, size_hint ? size_hint : rec.size_hint, id);
     if (rc != DM_OK) return rc;
     // Re-supply the saved prefix (cached, not re-hashed) through the ordinary range path: ring -> DMA -> extent.
-    int fd = rec.bytes ? open((base + ".part").c_str(), O_RDONLY) : -1;
-    bool ok = rec.bytes == 0 || fd >= 0;
-    if (ok && rec.bytes) {
+    // A blob too large for the arena continues verify-only: it retains nothing, so there is no prefix to load.
+    bool retains = true;
+    if (auto sp = find_stream(e, *id)) { std::lock_guard<std::mutex> g(sp->mu); retains = !sp->verify_only; }
+    int fd = rec.bytes && retains ? open((base + ".part").c_str(), O_RDONLY) : -1;
+    bool ok = rec.bytes == 0 || !retains || fd >= 0;
+    if (ok && rec.bytes && retains) {
         std::vector<uint8_t> buf(1u << 20);
         uint64_t off = 0;
         while (ok && off < rec.bytes) {
@@ -779,8 +810,15 @@ static int begin_finish(dm_engine *e, const std::shared_ptr<Stream> &sp, std::un
         if (rc != DM_OK) return rc;
         if (s->st == St::Finishing || s->st == St::Done) return DM_OK;      // someone else finished it while we waited
     }
-    rc = submit_slab(e, sp);
-    if (rc != DM_OK) return rc;
+    if (!pack_tiny_body(e, s)) {                       // tiny bodies share one DMA (struct Pack); everything else: its own
+        if (s->small_fill && !s->cur) {                  // no pack to be had right now: the private buffer's bytes need a slab
+            rc = take_slab(e, s, g);
+            if (rc != DM_OK) return rc;
+            if (s->st == St::Finishing || s->st == St::Done) return DM_OK;
+        }
+        rc = submit_slab(e, sp);
+        if (rc != DM_OK) return rc;
+    }
     while (!s->parts.empty()) {
         rc = submit_part(e, sp, s->parts.size() - 1);
         if (rc != DM_OK) return rc;
@@ -845,6 +883,7 @@ static int stream_abort_impl(dm_engine *e, uint64_t id)
         if (s->st == St::Done || s->st == St::Aborted) return fail(DM_ESTATE, "stream already closed");
         if (s->cur) { slab_put(e, s->cur); s->cur = nullptr; s->cur_fill = 0; }
         s->carry_fill = 0;
+        s->small.reset(); s->small_fill = 0; s->small_cap = 0;
         for (Stream::Part &pt : s->parts) slab_put(e, pt.slab);
         s->parts.clear();
         if (!s->staged.empty()) {            // their DMAs may be in flight: drain before the ring reuses them
@@ -855,6 +894,7 @@ static int stream_abort_impl(dm_engine *e, uint64_t id)
         }
         s->st = St::Aborted;
         free_now = s->jobs_inflight == 0;
+        if (free_now) pack_release_member(e, s);         // (a job already built keeps the pack until it is reaped)
     }
     if (free_now) {
         // A slab DMA into this extent may still be in flight; the range must not be handed to

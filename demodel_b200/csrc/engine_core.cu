@@ -230,6 +230,15 @@ Slab *slab_get(dm_engine *e)
     return s;
 }
 
+Slab *slab_try_get(dm_engine *e)
+{
+    std::lock_guard<std::mutex> g(e->slab_mu);
+    if (e->slab_free.empty()) return nullptr;
+    Slab *s = e->slab_free.back();
+    e->slab_free.pop_back();
+    return s;
+}
+
 void slab_put(dm_engine *e, Slab *s)
 {
     {
@@ -259,18 +268,24 @@ int take_slab(dm_engine *e, Stream *s, std::unique_lock<std::mutex> &g)
     s->cur = fresh;
     s->cur_fill = s->carry_fill;
     if (s->carry_fill) { memcpy(fresh->host, s->carry, s->carry_fill); s->carry_fill = 0; }
+    if (s->small_fill) {                        // a body that outgrew its private buffer continues in a real slab
+        memcpy(fresh->host, s->small.get(), s->small_fill);
+        s->cur_fill = s->small_fill;
+        s->small_fill = 0;
+    }
+    s->small.reset(); s->small_cap = 0;
     return DM_OK;
 }
 
 // Tell the pump this stream has new DMA'd bytes (or is finishing).  Stream mutex held.
-void mark_dirty(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *submitted)
+void mark_dirty(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *submitted, uint64_t landed_end)
 {
     const bool enqueue = !sp->queued;
     sp->queued = true;
     if (submitted) e->slabs_returning.fetch_add(1, std::memory_order_relaxed);
     {
         std::lock_guard<std::mutex> g(e->work_mu);
-        if (submitted) e->pending_slabs.push_back(submitted);
+        if (submitted) e->pending_slabs.push_back(SentSlab{submitted, landed_end ? sp : nullptr, landed_end});
         if (enqueue) e->dirty.push_back(sp);
     }
     e->work_cv.notify_one();
@@ -338,8 +353,9 @@ int submit_slab(dm_engine *e, const std::shared_ptr<Stream> &sp)
     int rc = dma_range(e, sp, slab, s->dma_issued, n);
     if (rc != DM_OK) return s->lost = rc;      // the staged bytes are gone: the stream can only be aborted now
     s->dma_issued += n;
+    const uint64_t seq_end = s->dma_issued;      // this slab's bytes end here (before any island is absorbed)
     absorb_islands(s);
-    mark_dirty(e, sp, slab);
+    mark_dirty(e, sp, slab, s->range_mode ? 0 : seq_end);
     if (s->followers) s->cv.notify_all();
     return DM_OK;
 }
@@ -350,6 +366,7 @@ int submit_part(dm_engine *e, const std::shared_ptr<Stream> &sp, size_t idx)
     Stream *s = sp.get();
     Stream::Part pt = s->parts[idx];
     s->parts.erase(s->parts.begin() + (long)idx);
+    s->range_mode = true;
     if (pt.fill == 0) { slab_put(e, pt.slab); return DM_OK; }
     e->st_ingested.fetch_add(pt.fill, std::memory_order_relaxed);
     int rc = dma_range(e, sp, pt.slab, pt.base, pt.fill);
@@ -377,6 +394,63 @@ bool range_taken(const Stream *s, uint64_t off, uint64_t len, const Stream::Part
     for (const Stream::Part &p : s->parts)
         if (&p != self && hits(p.base, p.base + p.fill)) return true;
     return false;
+}
+
+// ---- tiny bodies: shared pack slabs (struct Pack) ---------------------------------
+
+// Called by begin_finish with the stream mutex held.  True: the body now lives in the open pack, its own slab is
+// back in the ring and its extent is reserved; false: not eligible or no pack resources right now (the caller takes
+// the ordinary one-DMA-per-slab path, which is always correct).
+bool pack_tiny_body(dm_engine *e, Stream *s)
+{
+    const uint32_t n = s->cur ? s->cur_fill : s->small_fill;
+    const uint8_t *from = s->cur ? s->cur->host : s->small.get();
+    if (!from || n == 0 || n > e->tiny_max || s->verify_only || s->dma_issued || s->resume_base || s->carry_fill ||
+        !s->parts.empty() || !s->islands.empty() || e->pack_dev_base == nullptr)
+        return false;
+    if (ensure_capacity(e, s, n) != DM_OK) return false;              // (the ordinary path reports the ENOMEM)
+    uint64_t contig = 0;
+    if (!seg_at(e, s->extents, 0, &contig) || contig < n) return false;
+    const uint32_t need = (uint32_t)round_up(n, kAlign);
+    std::shared_ptr<Pack> pk;
+    uint32_t off;
+    {
+        std::lock_guard<std::mutex> g(e->pack_mu);
+        if (e->open_pack && e->open_pack->fill + need > e->cfg.slab_bytes) {
+            e->sealed_packs.push_back(e->open_pack);
+            e->open_pack.reset();
+        }
+        if (!e->open_pack) {
+            if (e->pack_dev_free.empty()) return false;
+            Slab *sl = slab_try_get(e);
+            if (!sl) return false;
+            auto np = std::make_shared<Pack>();
+            np->slab = sl;
+            np->dev = e->pack_dev_free.back();
+            e->pack_dev_free.pop_back();
+            e->open_pack = np;
+            e->st_packs++;
+        }
+        pk = e->open_pack;
+        off = pk->fill;
+        memcpy(pk->slab->host + off, from, n);
+        pk->fill += need;
+        pk->refs.fetch_add(1);
+    }
+    s->pack = pk; s->pack_off = off; s->pack_len = n;
+    if (s->cur) { slab_put(e, s->cur); s->cur = nullptr; s->cur_fill = 0; }     // the body's own slab is free again at once
+    s->small.reset(); s->small_fill = 0; s->small_cap = 0;
+    e->st_ingested.fetch_add(n, std::memory_order_relaxed);
+    e->st_packed++;
+    return true;
+}
+
+void pack_release_member(dm_engine *e, Stream *s)
+{
+    (void)e;
+    if (!s->pack) return;
+    s->pack->refs.fetch_sub(1);
+    s->pack.reset();
 }
 
 // ---- CAS commit --------------------------------------------------------------
@@ -610,6 +684,11 @@ void reap_cycle(dm_engine *e, Cycle &c)
         {
             std::lock_guard<std::mutex> g(sp->mu);
             if (c.err != cudaSuccess) sp->cuda_failed = true;
+            if (i < c.job_packs.size() && c.job_packs[i]) {        // tiny body: its bytes are in its own extent now
+                if (c.job_packs[i]->failed.load()) sp->cuda_failed = true;
+                sp->dma_issued = sp->hash_issued = sp->pack_len;
+                pack_release_member(e, sp.get());
+            }
             sp->jobs_inflight--;
             free_now = sp->st == St::Aborted && sp->jobs_inflight == 0;
             wake = sp->ckpt_waiter;
@@ -630,7 +709,7 @@ void reap_cycle(dm_engine *e, Cycle &c)
             e->done_cv.notify_one();
         }
     }
-    c.streams.clear(); c.is_final.clear();
+    c.streams.clear(); c.is_final.clear(); c.job_packs.clear();
     c.njobs = 0; c.bytes = 0; c.busy = false; c.err = cudaSuccess;
 }
 
@@ -639,7 +718,7 @@ void reap_cycle(dm_engine *e, Cycle &c)
 // bytes afterwards (or a job in flight) stay in `ready`.
 bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &ready)
 {
-    c.njobs = 0; c.bytes = 0;
+    c.njobs = 0; c.bytes = 0; c.needs_copy_wait = false;
     // Job length.  A launch is reaped as a whole, so it lasts as long as its longest lane and every lane
     // should be the same length: the quantum.  It is one slab while the streams are network-bound (each has
     // about a slab of backlog when it becomes ready), and grows to the smallest backlog among the streams
@@ -653,8 +732,10 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
         for (auto &sp : ready) {
             Stream *s = sp.get();
             std::lock_guard<std::mutex> g(s->mu);
-            if (s->st == St::Aborted || s->st == St::Done || s->final_issued || s->jobs_inflight || s->verify_only) continue;
-            const uint64_t backlog = s->dma_issued - s->hash_issued;
+            if (s->st == St::Aborted || s->st == St::Done || s->final_issued || s->jobs_inflight || s->verify_only || s->pack) continue;
+            // what a job could cover right now: landed bytes where the stream tracks them, else everything enqueued
+            const uint64_t upto = s->range_mode ? s->dma_issued : std::min(s->dma_issued, s->landed);
+            const uint64_t backlog = upto > s->hash_issued ? upto - s->hash_issued : 0;
             if (backlog >= slab) min_backlog = std::min(min_backlog, backlog);
         }
         if (min_backlog != ~0ull) quantum = std::min<uint64_t>(min_backlog / slab, kMaxJobSlabs) * slab;
@@ -667,13 +748,38 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
         // one job per stream in flight: its next job chains on the state this one writes
         if (s->jobs_inflight || c.njobs >= e->max_jobs) { again.push_back(sp); continue; }
         const bool finishing = s->st == St::Finishing;
-        uint64_t n = finishing ? (s->dma_issued - s->hash_issued) : ((s->dma_issued - s->hash_issued) & ~63ull);
-        if (!finishing && n == 0) { s->queued = false; continue; }
+        // How much can go into this job, and does the launch have to be ordered after the copy streams for it?
+        // Streams that track `landed` hash landed bytes only - no ordering, the launch starts at once - except for
+        // the tail of a finishing body, which is taken whole and ordered after its DMAs.
+        const uint64_t remaining = s->dma_issued - s->hash_issued;
+        const bool tracks = !s->verify_only && !s->pack && !s->range_mode;
+        bool wait_copy = !tracks;
+        uint64_t n;
+        if (tracks) {
+            const uint64_t lend = std::min(s->dma_issued, s->landed);
+            const uint64_t landed_n = lend > s->hash_issued ? lend - s->hash_issued : 0;
+            if (finishing && landed_n == remaining) n = remaining;
+            else if (finishing && landed_n < quantum) { n = remaining; wait_copy = true; }
+            else n = landed_n & ~63ull;
+        } else n = finishing ? remaining : (remaining & ~63ull);
+        if (!finishing && n == 0) { s->queued = false; continue; }      // (bytes still in flight re-queue the stream when they land)
         uint64_t contig = 0;
         uint8_t *src = nullptr;
         bool final = finishing;
         Slab *job_slab = nullptr;
-        if (s->verify_only) {
+        uint8_t *dst = nullptr;
+        std::shared_ptr<Pack> job_pack;
+        if (s->pack) {
+            // tiny body in a shared pack: wait for the pack's one DMA to be enqueued, then hash its piece out of the
+            // staging buffer while the kernel copies it into the body's own extent
+            if (!s->pack->dma_issued.load()) { again.push_back(sp); continue; }
+            if (s->pack->failed.load()) s->cuda_failed = true;
+            job_pack = s->pack;
+            src = job_pack->dev + s->pack_off;
+            dst = seg_at(e, s->extents, 0, &contig);
+            n = s->pack_len;
+            final = true;
+        } else if (s->verify_only) {
             if (!s->staged.empty()) {
                 job_slab = s->staged.front().first;
                 n = s->staged.front().second;               // whole slab; only the last may hold a partial block
@@ -685,31 +791,37 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
             else n = 0;
         } else {
             src = n ? seg_at(e, s->extents, s->hash_issued, &contig) : nullptr;
-            if (n > contig && n) { n = contig; final = false; }          // stop at the extent boundary
-            if (n > quantum) { n = quantum; final = false; }
+            if (n > contig && n) n = contig;                             // stop at the extent boundary
+            if (n > quantum) n = quantum;
+            if (n & 63 && s->hash_issued + n != s->dma_issued) n &= ~63ull;     // only the very last job may end in a partial block
+            final = finishing && s->hash_issued + n == s->dma_issued;
         }
         dm::HashJob &jb = c.h_jobs[c.njobs++];
-        jb.src = src; jb.dst = nullptr; jb.nbytes = n; jb.total_len = s->dma_issued; jb.slot = s->slot;
+        jb.src = src; jb.dst = dst; jb.nbytes = n; jb.total_len = job_pack ? n : s->dma_issued; jb.slot = s->slot;
         jb.flags = (s->hash_issued == 0 ? dm::JOB_INIT : 0u) | (final ? dm::JOB_FINAL : 0u);
         jb.one = 1; jb.pad_ = 0;
-        s->hash_issued += n;
+        if (!job_pack) s->hash_issued += n;            // (a packed body's counters move when its job is reaped)
         s->jobs_inflight++;
         if (final) s->final_issued = true;
         c.bytes += n;
         c.streams.push_back(sp);
         c.is_final.push_back(final ? 1 : 0);
         c.job_slabs.push_back(job_slab);
+        c.job_packs.push_back(job_pack);
+        if (wait_copy) c.needs_copy_wait = true;
         if (!final && (finishing || !s->staged.empty() || (!s->verify_only && ((s->dma_issued - s->hash_issued) & ~63ull)))) again.push_back(sp);
         else s->queued = false;
     }
     ready.swap(again);
     if (c.njobs == 0) return false;
 
-    // Everything whose DMA was enqueued before this point is covered by these events.
-    for (int i = 0; i < kCopyStreams; ++i) {
-        cudaEventRecord(c.copy_ev[i], e->copy_stream[i]);
-        cudaStreamWaitEvent(c.stream, c.copy_ev[i], 0);
-    }
+    // Jobs over landed bytes need nothing from the copy streams.  The others (range parts, verify-only staging, packs,
+    // the tail of a finishing body) are ordered after everything whose DMA was enqueued before this point.
+    if (c.needs_copy_wait)
+        for (int i = 0; i < kCopyStreams; ++i) {
+            cudaEventRecord(c.copy_ev[i], e->copy_stream[i]);
+            cudaStreamWaitEvent(c.stream, c.copy_ev[i], 0);
+        }
     // Launches overlap on the GPU, so what decides the kernel shape is how many jobs will be
     // co-resident (this launch + those still running), not the size of this launch alone.
     uint32_t resident = c.njobs;
@@ -726,8 +838,12 @@ bool run_cycle(dm_engine *e, Cycle &c, std::vector<std::shared_ptr<Stream>> &rea
         std::vector<std::shared_ptr<Stream>> st2(c.njobs);
         std::vector<uint8_t> fin2(c.njobs);
         std::vector<Slab *> sl2(c.njobs);
-        for (uint32_t i = 0; i < c.njobs; ++i) { c.h_jobs[i] = tmp[order[i]]; st2[i] = c.streams[order[i]]; fin2[i] = c.is_final[order[i]]; sl2[i] = c.job_slabs[order[i]]; }
-        c.streams.swap(st2); c.is_final.swap(fin2); c.job_slabs.swap(sl2);
+        std::vector<std::shared_ptr<Pack>> pk2(c.njobs);
+        for (uint32_t i = 0; i < c.njobs; ++i) {
+            c.h_jobs[i] = tmp[order[i]]; st2[i] = c.streams[order[i]]; fin2[i] = c.is_final[order[i]];
+            sl2[i] = c.job_slabs[order[i]]; pk2[i] = c.job_packs[order[i]];
+        }
+        c.streams.swap(st2); c.is_final.swap(fin2); c.job_slabs.swap(sl2); c.job_packs.swap(pk2);
     }
     // A failure anywhere here (or reported later by the end event) marks every stream of the launch:
     // their verdict becomes "not matched" and nothing is published (reap_cycle / complete_stream).
@@ -792,18 +908,31 @@ void pump_main(dm_engine *e)
     int n_inflight = 0;
     int b_head = 0, b_tail = 0, b_live = 0;
     std::vector<std::shared_ptr<Stream>> ready, inbox;
-    std::vector<Slab *> slabs;
+    std::vector<SentSlab> slabs;
+    std::vector<std::shared_ptr<Pack>> live_packs, sealed;
     int starve_ticks = 0;
     bool retry_ready = false;       // ready streams blocked only by their own in-flight job
     bool launched = false;
     for (;;) {
-        // 1. ring slabs whose DMA has completed go back to the writers
+        // 1. ring slabs whose DMA has completed go back to the writers, and their streams learn how far they have landed
+        bool landed_any = false;
         while (b_live) {
             SlabBatch &b = e->batches[b_tail];
             bool done = true;
             for (int i = 0; i < kCopyStreams; ++i) done = done && poll_event(b.ev[i]) == cudaSuccess;
             if (!done) break;
-            for (Slab *sl : b.slabs) slab_return(e, sl);
+            for (SentSlab &ss : b.slabs) {
+                slab_return(e, ss.slab);
+                if (!ss.sp) continue;
+                // the copy event behind this slab has fired: the stream's bytes up to ss.end are in HBM
+                bool wake = false;
+                {
+                    std::lock_guard<std::mutex> g(ss.sp->mu);
+                    if (ss.end > ss.sp->landed) ss.sp->landed = ss.end;
+                    if (!ss.sp->queued && (ss.sp->st == St::Open || ss.sp->st == St::Finishing)) { ss.sp->queued = true; wake = true; }
+                }
+                if (wake) { ready.push_back(ss.sp); landed_any = true; }
+            }
             b.slabs.clear(); b.busy = false;
             b_tail = (b_tail + 1) % kSlabBatches; --b_live;
         }
@@ -829,8 +958,8 @@ void pump_main(dm_engine *e)
         bool stopping;
         {
             std::unique_lock<std::mutex> g(e->work_mu);
-            const bool idle = !n_inflight && !b_live && ready.empty() && slabs.empty();
-            if (e->dirty.empty() && e->pending_slabs.empty() && !e->stop && !launched && !reaped) {
+            const bool idle = !n_inflight && !b_live && ready.empty() && slabs.empty() && live_packs.empty();
+            if (e->dirty.empty() && e->pending_slabs.empty() && !e->stop && !launched && !reaped && !landed_any) {
                 if (idle && e->ring_waiters.load() == 0)
                     e->work_cv.wait(g, [&] { return !e->dirty.empty() || !e->pending_slabs.empty() || e->stop || e->ring_starved.load(); });
                 else e->work_cv.wait_for(g, std::chrono::microseconds(40));
@@ -844,6 +973,30 @@ void pump_main(dm_engine *e)
         const bool fresh = !inbox.empty();
         for (auto &sp : inbox) ready.push_back(sp);
         inbox.clear();
+        // 3b. tiny-body packs: whatever gathered in the open pack since the last pass goes to the device with ONE copy
+        //     (after the inbox was taken: every stream in `ready` that sits in a pack has its pack sealed here)
+        {
+            std::lock_guard<std::mutex> g(e->pack_mu);
+            if (e->open_pack && e->open_pack->fill) { e->sealed_packs.push_back(e->open_pack); e->open_pack.reset(); }
+            sealed.swap(e->sealed_packs);
+        }
+        for (auto &pk : sealed) {
+            const cudaError_t err = cudaMemcpyAsync(pk->dev, pk->slab->host, pk->fill, cudaMemcpyHostToDevice, e->copy_stream[0]);
+            if (err != cudaSuccess) { (void)cudaGetLastError(); pk->failed.store(true); }
+            else e->st_h2d += pk->fill;
+            e->slabs_returning.fetch_add(1, std::memory_order_relaxed);
+            slabs.push_back(SentSlab{pk->slab, nullptr, 0});     // back to the ring with the next copy-event batch (step 4)
+            pk->slab = nullptr;
+            pk->dma_issued.store(true);
+            live_packs.push_back(pk);
+        }
+        sealed.clear();
+        for (size_t i = 0; i < live_packs.size();)      // staging buffers whose members have all been reaped (or aborted)
+            if (live_packs[i]->refs.load() == 0) {
+                { std::lock_guard<std::mutex> g(e->pack_mu); e->pack_dev_free.push_back(live_packs[i]->dev); }
+                live_packs[i] = live_packs.back();
+                live_packs.pop_back();
+            } else ++i;
         // 4. tag the newly DMA'd slabs with copy events
         if (!slabs.empty() && b_live < kSlabBatches) {
             SlabBatch &b = e->batches[b_head];
@@ -854,7 +1007,7 @@ void pump_main(dm_engine *e)
         }
         // 5. launch on a free slot.  With launches already running, let the ready set
         //    build up to a worthwhile size first (they will all fit in one launch anyway).
-        if (!ready.empty() && n_inflight < kCycles && (fresh || reaped || !retry_ready)) {
+        if (!ready.empty() && n_inflight < kCycles && (fresh || reaped || landed_any || !retry_ready)) {
             const uint64_t open_now = e->n_streams;
             const bool worthwhile = n_inflight == 0 || ready.size() * 8 >= open_now || ready.size() >= 4096;
             if (worthwhile) {
@@ -869,7 +1022,7 @@ void pump_main(dm_engine *e)
         }
         if (stopping && !n_inflight && !b_live && ready.empty() && slabs.empty()) {
             std::lock_guard<std::mutex> g(e->work_mu);
-            if (e->dirty.empty() && e->pending_slabs.empty()) break;
+            if (e->dirty.empty() && e->pending_slabs.empty()) break;       // (packs still referenced belong to streams nobody will finish)
         }
     }
 }

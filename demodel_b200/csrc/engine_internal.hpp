@@ -57,6 +57,8 @@ int fail_cuda(cudaError_t err, const char *where);
 constexpr uint64_t kAlign = 256;           // CAS extent granularity
 constexpr uint64_t kMaxGrow = 256ull << 20;
 constexpr int kCycles = 8;                 // concurrent hash launches, each on its own CUDA stream
+constexpr uint32_t kTinyMax = 64u << 10;    // bodies up to this size that arrive in one piece travel in shared "pack" slabs
+constexpr int kPackDevBufs = 64;           // device staging buffers for packs (slab_bytes each)
 constexpr uint32_t kMaxJobSlabs = 8;       // a job covers 1..8 slabs of backlog (run_cycle): fewer, longer launches when the hash is behind
 constexpr int kSlabBatches = 64;           // groups of DMA'd slabs waiting for their copy events
 constexpr int kStripes = 64;               // stream-table lock stripes
@@ -115,6 +117,21 @@ struct Blob {
 
 struct Slab { uint8_t *host; uint8_t *dev; };   // dev: same slab of the device-side mirror (verify-only streams)
 
+// Many tiny bodies, ONE H2D DMA.  A body of at most kTinyMax bytes that is still entirely in its first ring slab when it
+// finishes is copied into the engine's open pack (a ring slab shared by many such bodies) and gives its own slab
+// straight back; the pump DMAs the whole pack to a device staging buffer with one cudaMemcpyAsync, and each member's
+// final job hashes its piece from the staging buffer while copying it into the member's own CAS extent (the kernels'
+// fused copy).  Without this a 4 KiB manifest / config / tokenizer file costs a cudaMemcpyAsync of its own - the
+// driver call, not the bytes, was what capped small-body throughput.
+struct Pack {
+    Slab *slab = nullptr;            // host side, handed to the ordinary slab-return path once the DMA is enqueued
+    uint8_t *dev = nullptr;          // device staging buffer, back to the pool when the last member's job is reaped
+    uint32_t fill = 0;               // bytes used; members sit at 256-byte aligned offsets
+    std::atomic<uint32_t> refs{0};   // members whose job has not been reaped (or that have not been aborted)
+    std::atomic<bool> dma_issued{false};
+    std::atomic<bool> failed{false};
+};
+
 enum class St { Open, Finishing, Done, Aborted };
 
 struct Stream {
@@ -129,6 +146,13 @@ struct Stream {
     uint64_t received = 0;     // bytes accepted (count, any order)
     uint64_t dma_issued = 0;   // end of the contiguous run, starting at resume_base, whose H2D is enqueued
     uint64_t hash_issued = 0;  // bytes covered by launched jobs
+    // End of the contiguous run whose H2D copies have COMPLETED (the pump learns it from the copy events that return the
+    // slabs).  Jobs over landed bytes need no ordering against the copy streams, so a launch does not queue behind
+    // hundreds of MiB of other streams' DMAs that merely happen to sit ahead of its event in the copy FIFO (with a
+    // 1 GiB ring that was up to ~20 ms per launch while writers ran ahead of the hash).  Not maintained for streams
+    // that use range parts, verify-only staging or packs: those launches still wait on the copy events.
+    uint64_t landed = 0;
+    bool range_mode = false;   // dm_stream_write_at parts were used: `landed` is not the whole story
     Slab *cur = nullptr;       // sequential cursor: stages [dma_issued, dma_issued + cur_fill)
     uint32_t cur_fill = 0;
     // Range parts (dm_stream_write_at): out-of-order pieces staged per part, DMA'd to their place in
@@ -149,6 +173,13 @@ struct Stream {
     uint8_t carry[64];
     uint32_t carry_fill = 0;
     std::deque<std::pair<Slab *, uint32_t>> staged;
+    // A body announced (Content-Length) as at most tiny_max bytes never takes a ring slab: its bytes gather in this
+    // private buffer and go straight into a pack when it finishes.  Anything that needs a real slab (more bytes than
+    // announced, range parts, zero-copy windows, checkpoints) moves them into one first (take_slab).
+    std::unique_ptr<uint8_t[]> small;
+    uint32_t small_fill = 0, small_cap = 0;
+    std::shared_ptr<Pack> pack;      // tiny body travelling in a shared pack: [pack_off, pack_off + pack_len) of pack->dev
+    uint32_t pack_off = 0, pack_len = 0;
     std::vector<std::pair<std::string, std::string>> meta;   // dm_stream_set_meta
     uint32_t followers = 0;    // readers attached while the body is still arriving (request coalescing)
     uint32_t follow_reads = 0; // followers' copy-outs in flight: the extents must not be freed or handed over meanwhile
@@ -190,17 +221,23 @@ struct Cycle {
     dm::HashJob *d_jobs = nullptr;
     uint32_t njobs = 0;
     bool deep = false;
+    bool needs_copy_wait = false;    // some job reads bytes whose DMA may still be in flight
     uint64_t bytes = 0;
     std::vector<std::shared_ptr<Stream>> streams;   // one entry per job
     std::vector<Slab *> job_slabs;                  // verify-only jobs: the ring slab to release at reap
+    std::vector<std::shared_ptr<Pack>> job_packs;   // tiny-body jobs: the pack whose staging buffer they read
     std::vector<uint8_t> is_final;
     cudaError_t err = cudaSuccess;                  // first failure while building or running this launch
 };
 
+// A slab whose DMA has been enqueued, on its way back to the ring.  For a stream's sequential slabs it also says how
+// far the stream's bytes will have LANDED in HBM once the copy event behind it fires (Stream::landed).
+struct SentSlab { Slab *slab; std::shared_ptr<Stream> sp; uint64_t end; };
+
 struct SlabBatch {
     bool busy = false;
     cudaEvent_t ev[kCopyStreams]{};
-    std::vector<Slab *> slabs;
+    std::vector<SentSlab> slabs;
 };
 
 struct Bounce { uint8_t *host = nullptr; cudaStream_t stream{}; };
@@ -253,7 +290,7 @@ struct dm_engine {
     std::mutex work_mu;              // pump inbox
     std::condition_variable work_cv;
     std::vector<std::shared_ptr<Stream>> dirty;
-    std::vector<Slab *> pending_slabs;
+    std::vector<SentSlab> pending_slabs;
     std::atomic<bool> stop{false};   // set under work_mu; the spill threads read it under spill_mu
     std::atomic<int> ring_waiters{0};   // writers blocked in slab_get()
     // Slabs that are out of the ring but come back WITHOUT any writer doing anything: handed to the pump
@@ -300,6 +337,14 @@ struct dm_engine {
     uint32_t *ing_digests_h = nullptr;     // pinned
     uint32_t ing_cap = 0;
     cudaEvent_t ing_ev0{}, ing_ev1{};
+
+    std::mutex pack_mu;              // tiny-body packs (see struct Pack)
+    std::shared_ptr<Pack> open_pack;
+    std::vector<std::shared_ptr<Pack>> sealed_packs;     // full ones waiting for the pump
+    std::vector<uint8_t *> pack_dev_free;                // pool of kPackDevBufs device staging buffers
+    uint8_t *pack_dev_base = nullptr;
+    uint32_t tiny_max = 0;                               // min(kTinyMax, slab_bytes / 4); 0 = packs disabled
+    std::atomic<uint64_t> st_packed{0}, st_packs{0};
 
     std::mutex alias_mu;             // URL / ETag -> digest (dm_cache_alias_put/get); log = <cas_dir>/aliases.log
     std::unordered_map<std::string, Digest> aliases;
@@ -350,11 +395,14 @@ void lru_drop(dm_engine *e, Blob *b);         // e->mu held: the blob left HBM
 bool arena_alloc(dm_engine *e, uint64_t len, Extent *out);
 int ensure_capacity(dm_engine *e, Stream *s, uint64_t need);
 Slab *slab_get(dm_engine *e);
+Slab *slab_try_get(dm_engine *e);             // non-blocking: nullptr when the ring is empty
+bool pack_tiny_body(dm_engine *e, Stream *s);  // stream mutex held: move a finished tiny body into the open pack
+void pack_release_member(dm_engine *e, Stream *s);   // stream mutex held: this member no longer needs its pack
 void slab_put(dm_engine *e, Slab *s);
 void slab_return(dm_engine *e, Slab *s);      // slab_put for a slab that was counted in slabs_returning
 void ring_copy(dm_engine *e, void *dst, const void *src, size_t n);   // socket buffer -> ring slab
 int take_slab(dm_engine *e, Stream *s, std::unique_lock<std::mutex> &g);
-void mark_dirty(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *submitted);
+void mark_dirty(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *submitted, uint64_t landed_end = 0);
 int dma_range(dm_engine *e, const std::shared_ptr<Stream> &sp, Slab *slab, uint64_t base, uint32_t n);
 void absorb_islands(Stream *s);
 int submit_slab(dm_engine *e, const std::shared_ptr<Stream> &sp);

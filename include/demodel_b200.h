@@ -97,6 +97,8 @@ typedef struct dm_stats {
     int64_t  numa_node;           /* DM_F_NUMA_LOCAL: the node the engine bound itself to; -1 = not bound */
     uint64_t aliases;             /* URL / ETag -> digest entries (dm_cache_alias_put) */
     uint64_t suspended;           /* interrupted downloads saved under <cas_dir>/partial (dm_stream_suspend) */
+    uint64_t packed_bodies;       /* tiny bodies (<= 64 KiB, one piece) that shared a pack slab and its one H2D DMA */
+    uint64_t packs;               /* ... and how many such packs went to the device */
 } dm_stats;
 
 /* ---- engine lifetime (start.go:167-216) -------------------------------- */
@@ -117,6 +119,11 @@ int         dm_error_detail(dm_engine *e, uint64_t id, char *buf, size_t cap, si
 /* Kernel shape the engine picks for `n_resident` co-resident streams: streams per
  * warp, 1 = warp-per-stream (deep), 2..16 = group, 32 = lane-per-stream (wide).  Pure function. */
 uint32_t    dm_streams_per_warp(uint32_t n_resident);
+
+/* The kernel variant an engine uses unless DM_KERNEL_VARIANT overrides it: which = 0 the lane-per-stream (wide)
+ * kernel's `fma + 4*style`, which = 1 the round form of the warp-per-stream / group kernels.  Reported next to
+ * measurements (a profile taken with one variant says nothing about another).  Pure function. */
+uint32_t    dm_default_kernel_variant(int which);
 
 /* Digest-prefix sharding: which of n_shards engines owns a
  * blob.  Uses the leading 16 bits so any n_shards (not only powers of two)

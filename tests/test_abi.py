@@ -35,7 +35,7 @@ def test_abi_version_and_struct_layout():
     lib = demodel_b200.load()
     assert lib.dm_abi_version() == 2
     assert C.sizeof(_lib.DmConfig) == 48        # matches the C layout on LP64
-    assert C.sizeof(_lib.DmStats) == 23 * 8
+    assert C.sizeof(_lib.DmStats) == 25 * 8
 
 
 def test_strerror_covers_all_codes():

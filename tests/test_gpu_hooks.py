@@ -154,7 +154,6 @@ def test_suspended_download_survives_an_engine_restart(oracle, tmp_path):
         assert e2.fetch(want) == body.tobytes()                        # cached WHOLE: the saved prefix came back from disk
         assert e2.stats()["suspended"] == 0 and os.listdir(os.path.join(cas, "partial")) == []
         assert e2.stream_resume_saved(want, 0) is None
-        e2.cache_evict(want)
 
 
 def test_url_alias_survives_an_engine_restart(oracle, tmp_path):

@@ -50,9 +50,10 @@ def main():
     loop = rows[lds[0]:end + 1]
     ops = collections.Counter(r["op"] for r in loop)
     total = sum(max(r["stall"], 1) for r in loop)
-    print(f"{sys.argv[2]}: {len(loop)} instructions in the block loop: " + ", ".join(f"{k} {v}" for k, v in ops.most_common(8)))
-    print(f"  sum of ptxas stall counts = {total} cycles per 64-round block = {total / 64:.2f} cycles per round"
-          f" -> {1.965e9 / (total / 64) / 1e6:.1f} MB/s per stream at 1.965 GHz (phase 2 only)")
+    rounds = max(16, 16 * round(ops["SHF"] / 96))     # 6 rotations per round (+ a few address shifts): 64 (unrolled) or 16 (rolled) rounds per iteration
+    print(f"{sys.argv[2]}: {len(loop)} instructions in the loop ({rounds} rounds per iteration): " + ", ".join(f"{k} {v}" for k, v in ops.most_common(8)))
+    print(f"  sum of ptxas stall counts = {total} cycles per iteration = {total / rounds:.2f} cycles per round"
+          f" -> {1.965e9 / (total / rounds) / 1e6:.1f} MB/s per stream at 1.965 GHz (phase 2 only)")
 
 
 if __name__ == "__main__":
