@@ -79,6 +79,17 @@ def _cpu_quota():
         return None
 
 
+def _cfs_throttle():
+    """(nr_throttled, throttled_usec) of this cgroup (CFS bandwidth control), or None.  More runnable threads than the
+    CPU quota freeze the WHOLE group - the engine's pump and the CUDA driver threads included - for the rest of each
+    100 ms period once the quota is spent; the e2e leg reports how much of that it saw."""
+    try:
+        kv = dict(ln.split() for ln in open("/sys/fs/cgroup/cpu.stat").read().strip().splitlines())
+        return int(kv.get("nr_throttled", 0)), int(kv.get("throttled_usec", 0))
+    except Exception:
+        return None
+
+
 def _kernel_for(n):
     """Mirror of streams_per_warp_for() in demodel_b200/csrc/sha256_kernels.cuh (for the report only)."""
     for limit, name in ((640, "deep (1 stream/warp)"), (3072, "group (4 streams/warp)"), (6144, "group (8 streams/warp)"),
@@ -525,6 +536,7 @@ def main():
                 eng.cache_evict(d_)
         barrier()
         es0 = eng.stats()
+        thr0 = _cfs_throttle()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             dd, mm, _ = eng.proxy_drive(host, hoff, expect=expect, chunk=32768, concurrency=conc,
@@ -533,6 +545,7 @@ def main():
                 eng.cache_evict(d_)
         barrier()
         e_wall = time.perf_counter() - t0
+        thr1 = _cfs_throttle()
         assert dd == digs and all(mm)
         es1 = eng.stats()
         # cache-hit path: everything just ingested is served back out to host memory
@@ -559,6 +572,8 @@ def main():
                "launches_per_step": (es1["kernel_launches"] - es0["kernel_launches"]) / e2e_steps,
                "kernel_ms_sum_per_step": (es1["kernel_ms"] - es0["kernel_ms"]) / e2e_steps,
                "ring_waits_per_step": (es1["ring_waits"] - es0["ring_waits"]) / e2e_steps,
+               "cfs_throttled_ms_per_step": ((thr1[1] - thr0[1]) / 1e3 / e2e_steps) if thr0 and thr1 else None,
+               "cfs_throttled_periods_per_step": ((thr1[0] - thr0[0]) / e2e_steps) if thr0 and thr1 else None,
                "hit_serving": serve,
                "api": "dm_proxy_drive -> dm_stream_open/write/flush/finish, 32 KiB pieces, %d concurrent bodies on %d threads%s"
                       % (conc, drive_threads, ", zero-copy ring windows" if args.e2e_zero_copy else "")}

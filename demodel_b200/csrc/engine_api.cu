@@ -160,6 +160,7 @@ void dm_engine_destroy(dm_engine *e)
     if (e->ckpt_pinned) cudaFreeHost(e->ckpt_pinned);
     if (e->ing_ev0) cudaEventDestroy(e->ing_ev0);
     if (e->ing_ev1) cudaEventDestroy(e->ing_ev1);
+    if (e->ing_ev2) cudaEventDestroy(e->ing_ev2);
     if (e->pack_dev_base) cudaFree(e->pack_dev_base);
     if (e->d_states) cudaFree(e->d_states);
     if (e->h_digests) cudaFreeHost(e->h_digests);
@@ -207,6 +208,7 @@ static int engine_create(const dm_config *cfg, dm_engine **out)
     // turns them off, any other value moves the threshold (A/B runs).
     e->nt_copy_min = 16384;
     if (const char *v = getenv("DM_NT_COPY_MIN")) e->nt_copy_min = (uint32_t)strtoul(v, nullptr, 10);
+    if (const char *v = getenv("DM_SPLIT_MIN_BYTES")) e->split_min = strtoull(v, nullptr, 10);       // tuning / tests only
     if (!e->cfg.slab_bytes) e->cfg.slab_bytes = 1u << 20;
     if (!e->cfg.ring_bytes) e->cfg.ring_bytes = 256ull << 20;
     if (!e->cfg.max_streams) e->cfg.max_streams = 65536;
@@ -245,6 +247,7 @@ static int engine_create(const dm_config *cfg, dm_engine **out)
     CU_INIT(cudaHostAlloc(&e->ckpt_pinned, 64, cudaHostAllocDefault));
     CU_INIT(cudaEventCreate(&e->ing_ev0));
     CU_INIT(cudaEventCreate(&e->ing_ev1));
+    CU_INIT(cudaEventCreate(&e->ing_ev2));
 
     if ((e->cfg.flags & DM_F_NO_HBM_CAS) && !e->cfg.hbm_cas_bytes) e->cfg.hbm_cas_bytes = 1u << 20;   // only dm_ingest_device would use it
     if (!e->cfg.hbm_cas_bytes) {
@@ -413,6 +416,7 @@ static int stream_write_impl(dm_engine *e, uint64_t id, const void *buf, size_t 
     Stream *s = sp.get();
     std::unique_lock<std::mutex> g(s->mu);
     if (s->st != St::Open || s->window_out) return fail(DM_ESTATE, "stream not open for write");
+    if (s->lost != DM_OK) return fail(s->lost, kLostText);
     const uint8_t *p = static_cast<const uint8_t *>(buf);
     const uint32_t slab_bytes = e->cfg.slab_bytes;
     if (s->small_cap && !s->cur && s->small_fill + len <= s->small_cap) {     // announced-tiny body: private buffer, no slab

@@ -525,27 +525,56 @@ static int ingest_device_impl(dm_engine *e, const void *dev_base, const uint64_t
         std::vector<dm::HashJob> tmp(e->ing_jobs_h, e->ing_jobs_h + n);
         for (uint32_t i = 0; i < n; ++i) e->ing_jobs_h[i] = tmp[order[i]];   // slot keeps the caller's index
     }
-    cudaStream_t st = e->ingest_stream;
+    // A batch whose sizes are badly skewed (a few multi-GiB layers among thousands of small files) is two batches: the
+    // launch lasts as long as its longest chain, and a chain runs fastest with a warp of its own, so the long jobs
+    // (within 4x of the longest, at most one per sub-partition) get a warp-per-stream launch on a second CUDA
+    // stream while the rest go through the kernel their own count calls for.  (The stream path does this by itself:
+    // short bodies finish early and the pump sizes each later launch by who is left.)
+    uint32_t n_long = 0;
+    const bool forced = e->force_spw || (flags & (DM_ING_FORCE_WIDE | DM_ING_FORCE_DEEP | DM_ING_SPW_MASK));
+    if (spw > 1 && !forced && n > 1) {
+        const uint64_t longest = e->ing_jobs_h[0].nbytes;           // jobs are sorted longest first here
+        while (n_long < n && n_long < 592 && e->ing_jobs_h[n_long].nbytes * 4 >= longest) ++n_long;
+        if (n_long == n || longest < e->split_min) n_long = 0;      // not skewed, or nothing long enough to matter
+    }
+    const uint32_t n_rest = n - n_long;
+    const int spw_rest = n_long ? dm::streams_per_warp_for(n_rest) : spw;
+    cudaStream_t st = e->ingest_stream, st2 = e->util_stream;
     (void)cudaGetLastError();           // the caller's thread may carry a stale "not ready" from its own event polling
     cudaError_t err = cudaMemcpyAsync(e->ing_jobs_d, e->ing_jobs_h, sizeof(dm::HashJob) * (uint64_t)n, cudaMemcpyHostToDevice, st);
     if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev0, st);
-    if (err == cudaSuccess)
-        err = spw == 1 ? dm::launch_sha256_deep(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, e->variant_deep)
-            : spw == 32 ? dm::launch_sha256_wide(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, e->variant_wide)
-                        : dm::launch_sha256_group(e->ing_jobs_d, n, e->ing_states, e->ing_digests, st, spw, e->variant_deep);
+    if (err == cudaSuccess && n_long) {
+        err = cudaStreamWaitEvent(st2, e->ing_ev0, 0);              // the job table is in place
+        if (err == cudaSuccess) err = dm::launch_sha256_deep(e->ing_jobs_d, n_long, e->ing_states, e->ing_digests, st2, e->variant_deep);
+        if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev2, st2);
+    }
+    if (err == cudaSuccess) {
+        const dm::HashJob *rest = e->ing_jobs_d + n_long;
+        err = spw_rest == 1 ? dm::launch_sha256_deep(rest, n_rest, e->ing_states, e->ing_digests, st, e->variant_deep)
+            : spw_rest == 32 ? dm::launch_sha256_wide(rest, n_rest, e->ing_states, e->ing_digests, st, e->variant_wide)
+                             : dm::launch_sha256_group(rest, n_rest, e->ing_states, e->ing_digests, st, spw_rest, e->variant_deep);
+    }
     if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev1, st);
+    if (err == cudaSuccess && n_long) err = cudaStreamWaitEvent(st, e->ing_ev2, 0);       // digests of both launches
     if (err == cudaSuccess) err = cudaMemcpyAsync(e->ing_digests_h, e->ing_digests, 32ull * n, cudaMemcpyDeviceToHost, st);
     if (err == cudaSuccess) err = cudaStreamSynchronize(st);
     if (err != cudaSuccess) {
         cudaStreamSynchronize(st);      // whatever was enqueued before the failure still uses the job table and the extents
+        cudaStreamSynchronize(st2);
         cleanup();
         return fail_cuda(err, "dm_ingest_device launch");
     }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e->ing_ev0, e->ing_ev1);
+    if (n_long) {                       // two overlapping launches: the pass lasted until the later one ended
+        float ms2 = 0.f;
+        cudaEventElapsedTime(&ms2, e->ing_ev0, e->ing_ev2);
+        ms = std::max(ms, ms2);
+        e->st_launches++; e->st_deep++;
+    }
     if (kernel_ms) *kernel_ms = ms;
     { std::lock_guard<std::mutex> g(e->stat_mu); e->st_kernel_ms += ms; }
-    e->st_launches++; (spw == 1 ? e->st_deep : spw == 32 ? e->st_wide : e->st_group)++;
+    e->st_launches++; (spw_rest == 1 ? e->st_deep : spw_rest == 32 ? e->st_wide : e->st_group)++;
     e->st_hashed += total;
     std::vector<Verified> good;
     std::vector<Extent> bad;

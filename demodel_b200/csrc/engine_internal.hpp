@@ -299,6 +299,7 @@ struct dm_engine {
     // recalls partly filled slabs from other streams only when it is zero, i.e. when every slab is being
     // filled by somebody and nothing would otherwise move (more live streams than slabs).
     std::atomic<int> slabs_returning{0};
+    uint64_t split_min = 8u << 20;      // dm_ingest_device splits a skewed batch only if its longest blob is at least this long
     uint32_t nt_copy_min = 0;           // dm_stream_write pieces >= this many bytes use streaming stores (0 = never)
     std::thread pump;
     Cycle cycles[kCycles];
@@ -336,7 +337,7 @@ struct dm_engine {
     dm::HashJob *ing_jobs_d = nullptr;
     uint32_t *ing_digests_h = nullptr;     // pinned
     uint32_t ing_cap = 0;
-    cudaEvent_t ing_ev0{}, ing_ev1{};
+    cudaEvent_t ing_ev0{}, ing_ev1{}, ing_ev2{};
 
     std::mutex pack_mu;              // tiny-body packs (see struct Pack)
     std::shared_ptr<Pack> open_pack;

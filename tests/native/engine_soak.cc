@@ -534,6 +534,52 @@ static void driver_phase(bool verify_only)
     dm_engine_destroy(e);
 }
 
+// a partial slab recalled by the PUMP whose DMA cannot be placed (arena full while an
+// unknown-size body grows) used to drop the bytes silently - the writer carried on and finish() succeeded over a
+// truncated body.  Built deterministically: arena of exactly three slabs, ring of four.
+static void lost_bytes_are_sticky()
+{
+    dm_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = sizeof cfg;
+    const uint32_t slab = 64u << 10;
+    cfg.hbm_cas_bytes = 3 * slab; cfg.ring_bytes = 4 * slab; cfg.slab_bytes = slab; cfg.max_streams = 16;
+    dm_engine *e = nullptr;
+    CHECK(dm_engine_create(&cfg, &e) == DM_OK);
+    std::vector<uint8_t> buf(4 * slab, 0x5c);
+    uint64_t a = 0, b = 0, c = 0;
+    CHECK(dm_stream_open(e, nullptr, 0, &a) == DM_OK);                       // A: size unknown
+    CHECK(dm_stream_write(e, a, buf.data(), slab + 100) == DM_OK);           // one slab sent (extent: 1 slab), 100 B staged
+    CHECK(dm_stream_open(e, nullptr, 2 * slab, &b) == DM_OK);                // B: reserves the rest of the arena
+    CHECK(dm_stream_write_at(e, b, 1000, buf.data(), 10) == DM_OK);          // ... and pins the other three ring slabs
+    CHECK(dm_stream_write_at(e, b, 5000, buf.data(), 10) == DM_OK);
+    CHECK(dm_stream_write_at(e, b, 9000, buf.data(), 10) == DM_OK);
+    CHECK(dm_stream_open(e, nullptr, 0, &c) == DM_OK);
+    int rc_c = 1;
+    std::thread t([&] { rc_c = dm_stream_write(e, c, buf.data(), 10); });    // blocks: the ring is empty and nothing is in flight
+    int rc = DM_OK;
+    for (int i = 0; i < 4000 && rc == DM_OK; ++i) {                          // the pump recalls A's 100 bytes: no room for them
+        std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        rc = dm_stream_write(e, a, buf.data(), 0);
+    }
+    t.join();
+    CHECK(rc == DM_ENOMEM);                                                  // the writer is told on its next call ...
+    uint8_t got[32];
+    int matched = -1;
+    CHECK(dm_stream_finish(e, a, got, &matched) == DM_ENOMEM);               // ... and the truncated body can not be finished
+    char why[160];
+    size_t n = 0;
+    CHECK(dm_error_detail(e, a, why, sizeof why, &n) == DM_OK && strstr(why, "dropped") != nullptr);
+    CHECK(dm_stream_abort(e, a) == DM_OK);
+    CHECK(rc_c == DM_OK);                                                    // C got a recalled slab
+    CHECK(dm_stream_abort(e, c) == DM_OK);
+    CHECK(dm_stream_abort(e, b) == DM_OK);
+    dm_stats st;
+    for (int i = 0; i < 500; ++i) { dm_engine_stats(e, &st); if (st.ring_slabs_free == st.ring_slabs_total) break; std::this_thread::sleep_for(std::chrono::milliseconds(2)); }
+    CHECK(st.ring_slabs_free == st.ring_slabs_total && st.open_streams == 0 && st.blobs_committed == 0);
+    dm_engine_destroy(e);
+}
+
 // Shutdown with transfers in flight: the proxy is stopped while bodies are half way and hits are being served.
 // Destroy must not hang, crash or touch freed memory (ASan), whatever state the streams and readers are in.
 static void destroy_with_open_handles(const char *cas_dir)
@@ -680,6 +726,7 @@ int main(int argc, char **argv)
     }
     if (!failures.load() && !g_inject) driver_phase(verify_only);
     if (!failures.load() && !verify_only && !g_inject) destroy_with_open_handles(cas_dir);
+    if (!failures.load() && !verify_only && !g_inject && !cas_dir) lost_bytes_are_sticky();
     if (failures.load() || !clean) { printf("ENGINE SOAK FAILED\n"); return 1; }
     printf("ENGINE SOAK OK\n");
     return 0;
