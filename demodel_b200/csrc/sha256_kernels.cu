@@ -228,6 +228,10 @@ constexpr int kWideThreads = 128;
 //   2  one 128-byte line per iteration, rounds rolled 16 at a time          (~20 KB)
 //   3  one 64-byte block per iteration, rolled                              (~10 KB)
 //   4  as 2, with the loads software-pipelined half a line ahead
+//   5  as 2, with every lane's next 128-byte line fetched by cp.async into its own row of shared memory (two
+//      stages) while the current line is hashed: the line load leaves the register file and its ~600-cycle
+//      latency off the scoreboard (ncu on style 2: long_scoreboard 0.53 per issue on the first use of the line)
+constexpr int kWideRow = 144;                 // bytes per lane row in shared memory: 128 + 16 pad -> conflict-free LDS.128
 template <int kFma, int kStyle>
 __global__ void __launch_bounds__(kWideThreads, kStyle == 4 ? 5 : 1)
 sha256_wide_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *__restrict__ states,
@@ -244,7 +248,42 @@ sha256_wide_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
     uint4 *q = reinterpret_cast<uint4 *>(jb.dst);
     const bool copy = q != nullptr;
     uint32_t rem;
-    if constexpr (kStyle == 4) {
+    if constexpr (kStyle == 5) {
+        __shared__ __align__(16) uint8_t rows[2][kWideThreads * kWideRow];
+        const uint32_t my = threadIdx.x * kWideRow;
+        auto fetch = [&](int stage, const uint4 *from) {      // this lane's next line -> its row of `stage`, asynchronously
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&rows[stage][my]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16u * i), "l"(from + i) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        uint64_t npair = jb.nbytes >> 7;
+        if (npair) fetch(0, p);
+        int stage = 0;
+#pragma unroll 1
+        for (; npair != 0; --npair) {
+            if (npair > 1) { fetch(stage ^ 1, p + 8); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const uint4 *row = reinterpret_cast<const uint4 *>(&rows[stage][my]);     // only this lane ever touches its row
+            uint32_t w[16];
+            {
+                const uint4 a = row[0], b = row[1], c = row[2], d = row[3];
+                if (copy) { st_stream(q, a); st_stream(q + 1, b); st_stream(q + 2, c); st_stream(q + 3, d); }
+                unpack_be(w, a, b, c, d);
+            }
+            compress_rolled<kFma>(s, w, k);
+            {
+                const uint4 a = row[4], b = row[5], c = row[6], d = row[7];
+                if (copy) { st_stream(q + 4, a); st_stream(q + 5, b); st_stream(q + 6, c); st_stream(q + 7, d); q += 8; }
+                unpack_be(w, a, b, c, d);
+            }
+            compress_rolled<kFma>(s, w, k);
+            p += 8;
+            stage ^= 1;
+        }
+        rem = (uint32_t)(jb.nbytes & 127u);
+    } else if constexpr (kStyle == 4) {
         // rolled rounds, loads software-pipelined half a line ahead: the second half of the
         // current line and the first half of the next one are in flight during a compression
         uint64_t npair = jb.nbytes >> 7;
@@ -597,6 +636,7 @@ cudaError_t launch_sha256_wide(const HashJob *jobs, uint32_t njobs, uint32_t *st
     DM_W(0, 0) DM_W(1, 0) DM_W(2, 0) DM_W(0, 1) DM_W(1, 1) DM_W(2, 1)
     DM_W(0, 2) DM_W(1, 2) DM_W(2, 2) DM_W(0, 3) DM_W(1, 3) DM_W(2, 3)
     DM_W(0, 4) DM_W(1, 4) DM_W(2, 4)
+    DM_W(1, 5)
 #undef DM_W
     default: launch_wide_t<kDefaultWideVariant % 4, kDefaultWideVariant / 4>(jobs, njobs, states, digests, stream); break;
     }
