@@ -10,23 +10,25 @@
 //                        whole 128-byte line (two blocks) per iteration.  The
 //                        shipped variant rolls the rounds 16 at a time (round
 //                        constants from the constant bank; the fully unrolled
-//                        form stalled on the instruction cache) and issues the
-//                        additions on the FMA pipe.  Bound by the ALU pipe
-//                        (one warp-instruction per 2 cycles per sub-partition):
-//                        <= 1.15 TB/s per B200, 0.95 measured; needs > ~10^4
-//                        streams to fill the chip.
+//                        form stalled on the instruction cache), issues the
+//                        additions on the FMA pipe, and stages every lane's next
+//                        line in shared memory with cp.async.  Bound by the ALU
+//                        pipe (one warp-instruction per 2 cycles per
+//                        sub-partition): <= 1.15 TB/s per B200, 1.02 measured;
+//                        needs > ~10^4 streams to fill the chip.
 //   sha256_deep_kernel   one warp per stream, for few live streams.  SHA-256's
 //                        serial chain is only the 64 rounds; the message
 //                        schedule is state-independent.  The 32 lanes expand
 //                        the schedules of 32 consecutive blocks in parallel
 //                        (coalesced 2 KiB load) and stage W[t]+K[t] in shared
 //                        memory; then the warp runs the 32x64 dependent rounds
-//                        reading one broadcast LDS.128 per 4 rounds.  ~1.6x the
-//                        per-stream rate of the lane-per-stream form (63 MB/s).
+//                        reading one broadcast LDS.128 per 4 rounds.  ~1.9x the
+//                        per-stream rate of the lane-per-stream form (76 MB/s).
 //   sha256_group_kernel  S = 2/4/8/16 streams per warp: the deep kernel's two
 //                        phases with lane = block_slot * S + stream, so S round
-//                        chains advance per instruction.  Wins between ~640 and
-//                        ~12 000 streams.
+//                        chains advance per instruction.  Wins between 593 and
+//                        ~9 500 streams (S = the smallest that keeps one warp per
+//                        sub-partition).
 //
 // All optionally write every byte they read to `dst` (the blob's CAS
 // extent), so hash-and-cache moves 1 B read + 1 B written per blob byte;

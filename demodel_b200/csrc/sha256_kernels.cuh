@@ -36,7 +36,9 @@ cudaError_t launch_sha256_wide(const HashJob *jobs, uint32_t njobs, uint32_t *st
                                uint32_t *digests, cudaStream_t stream, int variant);
 cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *states,
                                uint32_t *digests, cudaStream_t stream, int variant);
-constexpr int kDefaultWideVariant = 9;   // fma 1 + style 2
+// fma 1 + style 5: rolled rounds, additions on the FMA pipe, every lane's next 128-byte line staged by cp.async in its own
+// shared-memory row.  Measured on B200, 151 552 streams x 112 KiB: style 2 (variant 9, round 1) 18.25 ms, style 5 17.07 ms.
+constexpr int kDefaultWideVariant = 21;
 // S streams per warp, S in {2,4,8,16}: the middle ground between deep and wide.  `variant` is the deep
 // kernel's (the serial phase is the same code): 4..7 = the short-chain rounds, anything else = ptxas' ordering.
 cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *states,
@@ -46,11 +48,14 @@ cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *s
 // each of the 592 sub-partitions.  Returns streams per warp: 1 = deep, 32 = wide.
 inline int streams_per_warp_for(uint32_t njobs)
 {
-    // crossovers measured on B200 (tools/ab_group.sh, profiles/r01_streams_per_warp_sweep.txt)
-    if (njobs <= 640) return 1;
-    if (njobs <= 3072) return 4;
-    if (njobs <= 6144) return 8;
-    if (njobs <= 12288) return 16;
+    // One warp per sub-partition (148 SMs x 4) for as long as that is possible: the smallest S whose njobs / S warps
+    // still fit one per sub-partition; past 16 streams per warp, a lane per stream.  Measured on B200 with the
+    // variant-7 round (tools/ab_group.sh, profiles/r02_streams_per_warp_sweep.txt): a second warp on a sub-partition
+    // halves both (640 streams, one warp each: 340 ms; two per warp: 206 ms), and every crossover sits where the
+    // warp count passes 592.
+    constexpr uint32_t kSubPartitions = 592;
+    for (int s = 1; s <= 16; s *= 2)
+        if ((njobs + s - 1) / s <= kSubPartitions) return s;
     return 32;
 }
 // 7 = short-chain round with e' on the FMA pipe and a' as one IADD3 (sha256_round.cuh): measured on B200
