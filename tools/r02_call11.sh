@@ -4,6 +4,7 @@
 # kernel: racecheck), ncu of the wide kernel as shipped, soak
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.txt 2>&1
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02_gputests.txt 2>&1
 echo "pytest rc=$?" >> gpurun_out/r02_gputests.txt
 timeout 400 python bench.py --steps 3 --warmup 3 > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err
