@@ -30,7 +30,7 @@ import demodel_b200
 lib = demodel_b200.load()
 variant = f"{lib.dm_default_kernel_variant(0)},{lib.dm_default_kernel_variant(1)}"
 tot = int(vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"])
-json.dump({"hf_lfs_256x64MiB": {"bytes": tot, "kernel_variant": variant, "kernel": re.sub(r"\(.*", "", kernel),
+json.dump({"hf_lfs_256x64MiB": {"bytes": tot, "kernel_variant": variant, "family": "wide" if "wide" in kernel else "deep", "kernel": re.sub(r"\(.*", "", kernel),
            "source": "profiles/r02_dram_default.csv: dram__bytes_read.sum + dram__bytes_write.sum of one launch at the full default "
                      f"workload ({int(vals['dram__bytes_read.sum'])} + {int(vals['dram__bytes_write.sum'])} B); algorithmic 2 x 17179869184 B"}},
           open("gpurun_out/roofline_traffic.json", "w"), indent=1)
