@@ -200,7 +200,7 @@ static int engine_create(const dm_config *cfg, dm_engine **out)
     if (const char *v = getenv("DM_KERNEL_VARIANT")) {   // "wide,deep" variant numbers; experiments only
         int w = -1, d = -1;
         if (sscanf(v, "%d,%d", &w, &d) >= 1) {
-            if (w >= 0 && w < 28) e->variant_wide = w;
+            if (w >= 0 && w < 24) e->variant_wide = w;
             if (d >= 0 && d <= 7) e->variant_deep = d;   // 4..7 = short-chain rounds (deep and group kernels)
         }
     }

@@ -250,7 +250,7 @@ sha256_wide_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
     uint4 *q = reinterpret_cast<uint4 *>(jb.dst);
     const bool copy = q != nullptr;
     uint32_t rem;
-    if constexpr (kStyle == 5 || kStyle == 6) {
+    if constexpr (kStyle == 5) {
         __shared__ __align__(16) uint8_t rows[2][kWideThreads * kWideRow];
         const uint32_t my = threadIdx.x * kWideRow;
         auto fetch = [&](int stage, const uint4 *from) {      // this lane's next line -> its row of `stage`, asynchronously
@@ -269,30 +269,20 @@ sha256_wide_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
             const uint4 *row = reinterpret_cast<const uint4 *>(&rows[stage][my]);     // only this lane ever touches its row
             uint32_t w[16];
-            if constexpr (kStyle == 5) {
-                {
-                    const uint4 a = row[0], b = row[1], c = row[2], d = row[3];
-                    if (copy) { st_stream(q, a); st_stream(q + 1, b); st_stream(q + 2, c); st_stream(q + 3, d); }
-                    unpack_be(w, a, b, c, d);
-                }
-                compress_rolled<kFma>(s, w, k);
-                {
-                    const uint4 a = row[4], b = row[5], c = row[6], d = row[7];
-                    if (copy) { st_stream(q + 4, a); st_stream(q + 5, b); st_stream(q + 6, c); st_stream(q + 7, d); q += 8; }
-                    unpack_be(w, a, b, c, d);
-                }
-                compress_rolled<kFma>(s, w, k);
-            } else {
-                // style 6: the two blocks of the line go through ONE copy of the compression code (half the loop body:
-                // ncu on style 5 still shows no_instruction 0.077 per issue)
-#pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    const uint4 a = row[4 * h], b = row[4 * h + 1], c = row[4 * h + 2], d = row[4 * h + 3];
-                    if (copy) { st_stream(q, a); st_stream(q + 1, b); st_stream(q + 2, c); st_stream(q + 3, d); q += 4; }
-                    unpack_be(w, a, b, c, d);
-                    compress_rolled<kFma>(s, w, k);
-                }
+            {
+                const uint4 a = row[0], b = row[1], c = row[2], d = row[3];
+                if (copy) { st_stream(q, a); st_stream(q + 1, b); st_stream(q + 2, c); st_stream(q + 3, d); }
+                unpack_be(w, a, b, c, d);
             }
+            compress_rolled<kFma>(s, w, k);
+            {
+                const uint4 a = row[4], b = row[5], c = row[6], d = row[7];
+                if (copy) { st_stream(q + 4, a); st_stream(q + 5, b); st_stream(q + 6, c); st_stream(q + 7, d); q += 8; }
+                unpack_be(w, a, b, c, d);
+            }
+            compress_rolled<kFma>(s, w, k);
+            // (running the two blocks through ONE copy of the compression code - half the loop body, 78 registers - was
+            //  measured too: 17.12 ms against 17.05 ms, no gain)
             p += 8;
             stage ^= 1;
         }
@@ -650,7 +640,7 @@ cudaError_t launch_sha256_wide(const HashJob *jobs, uint32_t njobs, uint32_t *st
     DM_W(0, 0) DM_W(1, 0) DM_W(2, 0) DM_W(0, 1) DM_W(1, 1) DM_W(2, 1)
     DM_W(0, 2) DM_W(1, 2) DM_W(2, 2) DM_W(0, 3) DM_W(1, 3) DM_W(2, 3)
     DM_W(0, 4) DM_W(1, 4) DM_W(2, 4)
-    DM_W(1, 5) DM_W(1, 6)
+    DM_W(1, 5)
 #undef DM_W
     default: launch_wide_t<kDefaultWideVariant % 4, kDefaultWideVariant / 4>(jobs, njobs, states, digests, stream); break;
     }
