@@ -333,7 +333,7 @@ int dm_engine_stats(dm_engine *e, dm_stats *o)
     o->launches_group = e->st_group;
     { std::lock_guard<std::mutex> g(e->slab_mu); o->ring_slabs_total = e->slab_store.size(); o->ring_slabs_free = e->slab_free.size(); }
     for (int k = 0; k < kStripes; ++k) { std::lock_guard<std::mutex> g(e->reader_mu[k]); o->open_readers += e->readers[k].size(); }
-    { std::lock_guard<std::mutex> g(e->mu); o->free_stream_slots = e->free_slots.size(); }
+    { std::lock_guard<std::mutex> g(e->slot_mu); o->free_stream_slots = e->free_slots.size(); }
     o->numa_node = e->numa_node;
     { std::lock_guard<std::mutex> g(e->alias_mu); o->aliases = e->aliases.size(); }
     o->suspended = e->n_suspended;
@@ -352,18 +352,18 @@ static int stream_open_impl(dm_engine *e, const uint8_t expect[32], uint64_t siz
     auto sp = std::make_shared<Stream>();
     if (expect) { sp->has_expect = true; memcpy(sp->expect.b, expect, 32); }
     {
-        std::lock_guard<std::mutex> g(e->mu);
+        std::lock_guard<std::mutex> g(e->slot_mu);
         if (e->free_slots.empty()) return fail(DM_ENOMEM, "max_streams reached");
         sp->slot = e->free_slots.back();
         e->free_slots.pop_back();
-        sp->id = e->next_id++;
     }
+    sp->id = e->next_id.fetch_add(1);
     sp->verify_only = (e->cfg.flags & DM_F_NO_HBM_CAS) != 0;
     if (!sp->verify_only && size_hint > e->cfg.hbm_cas_bytes) {
         // can never be cached here: still verify it, through the device mirror of the ring
         int rc = ensure_dev_ring(e);
         if (rc != DM_OK) {
-            std::lock_guard<std::mutex> g2(e->mu);
+            std::lock_guard<std::mutex> g2(e->slot_mu);
             e->free_slots.push_back(sp->slot);
             return rc;
         }
@@ -374,7 +374,7 @@ static int stream_open_impl(dm_engine *e, const uint8_t expect[32], uint64_t siz
         std::lock_guard<std::mutex> g(sp->mu);
         Extent x;
         if (!arena_alloc(e, size_hint, &x)) {
-            std::lock_guard<std::mutex> g2(e->mu);
+            std::lock_guard<std::mutex> g2(e->slot_mu);
             e->free_slots.push_back(sp->slot);
             return fail(DM_ENOMEM, "HBM CAS arena exhausted");
         }

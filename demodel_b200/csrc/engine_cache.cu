@@ -55,11 +55,7 @@ static int cache_open_impl(dm_engine *e, const uint8_t digest[32], uint64_t *rea
             fclose(mf);
         }
     }
-    uint64_t id;
-    {
-        std::lock_guard<std::mutex> g(e->mu);
-        id = e->next_id++;
-    }
+    const uint64_t id = e->next_id.fetch_add(1);
     {
         std::lock_guard<std::mutex> g(e->reader_mu[id % kStripes]);
         e->readers[id % kStripes][id] = r;
@@ -316,7 +312,7 @@ static int cache_follow_impl(dm_engine *e, const uint8_t digest[32], uint64_t *r
         if (it == e->inflight.end()) return DM_ENOENT;
         r->follow = it->second.lock();
         if (!r->follow) { e->inflight.erase(it); return DM_ENOENT; }
-        id = e->next_id++;
+        id = e->next_id.fetch_add(1);
     }
     r->size = r->follow->size_hint;
     {

@@ -638,10 +638,10 @@ void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint
     const bool whole = s->resume_base == 0 ||
                        (s->prefix_cover.size() == 1 && s->prefix_cover.begin()->first == 0 &&
                         s->prefix_cover.begin()->second >= s->resume_base);
+    std::vector<std::pair<std::string, std::string>> meta;
+    meta.swap(s->meta);
     g.unlock();
     std::shared_ptr<Blob> b;
-    std::vector<std::pair<std::string, std::string>> meta;
-    g.lock(); meta.swap(s->meta); g.unlock();
     if (matched && whole && !s->verify_only) b = publish(e, d, size, ext, &meta);
     else { free_extents(e, ext); if (!matched) e->st_mismatch++; }
     g.lock();
@@ -654,21 +654,24 @@ void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint
 void completer_main(dm_engine *e)
 {
     cudaSetDevice(e->device);
+    std::vector<dm_engine::DoneItem> batch;
     for (;;) {
-        dm_engine::DoneItem it;
         {
             std::unique_lock<std::mutex> g(e->done_mu);
             e->done_cv.wait(g, [&] { return !e->done_q.empty() || e->done_stop; });
             if (e->done_q.empty()) return;
-            it = std::move(e->done_q.front());
-            e->done_q.pop_front();
+            // a share of what is queued (the other completion thread takes the rest), at most 64 per lock
+            size_t take = std::min<size_t>(64, (e->done_q.size() + kCompleters - 1) / kCompleters);
+            while (take--) { batch.push_back(std::move(e->done_q.front())); e->done_q.pop_front(); }
         }
-        complete_stream(e, it.sp, it.words);
+        for (auto &it : batch) complete_stream(e, it.sp, it.words);
+        batch.clear();
     }
 }
 
 void reap_cycle(dm_engine *e, Cycle &c)
 {
+    std::vector<dm_engine::DoneItem> finished;          // handed to the completion threads under ONE lock at the end
     float ms = 0.f;
     if (c.njobs) {
         cudaEventElapsedTime(&ms, c.k_start, c.k_end);
@@ -699,15 +702,22 @@ void reap_cycle(dm_engine *e, Cycle &c)
             cudaStreamSynchronize(e->copy_stream[sp->id % kCopyStreams]);
             { std::unique_lock<std::mutex> g(sp->mu); wait_follow_reads(sp.get(), g); }
             free_extents(e, sp->extents);
-            std::lock_guard<std::mutex> g(e->mu);
+            std::lock_guard<std::mutex> g(e->slot_mu);
             e->free_slots.push_back(sp->slot);
         } else if (c.is_final[i]) {
             dm_engine::DoneItem it;
             it.sp = sp;
             memcpy(it.words, e->h_digests + 8ull * sp->slot, sizeof it.words);
-            { std::lock_guard<std::mutex> g(e->done_mu); e->done_q.push_back(std::move(it)); }
-            e->done_cv.notify_one();
+            finished.push_back(std::move(it));
         }
+    }
+    if (!finished.empty()) {
+        const bool many = finished.size() > 1;
+        {
+            std::lock_guard<std::mutex> g(e->done_mu);
+            for (auto &it : finished) e->done_q.push_back(std::move(it));
+        }
+        if (many) e->done_cv.notify_all(); else e->done_cv.notify_one();
     }
     c.streams.clear(); c.is_final.clear(); c.job_packs.clear();
     c.njobs = 0; c.bytes = 0; c.busy = false; c.err = cudaSuccess;
@@ -1175,16 +1185,17 @@ void drop_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, bool release_s
         erased = e->streams[k].erase(sp->id) != 0;
         if (erased) e->n_streams--;
     }
-    {
+    // exactly one caller takes the stream out of the table, and only that one may give its state slot
+    // back (two finishes on one id, or a finish racing an abort, would otherwise release it twice and
+    // two later streams would share one state / digest slot)
+    if (release_slot && erased) {
+        std::lock_guard<std::mutex> g(e->slot_mu);
+        e->free_slots.push_back(sp->slot);
+    }
+    if (sp->has_expect) {                            // only streams with an expected digest are in the follow index
         std::lock_guard<std::mutex> g(e->mu);
-        // exactly one caller takes the stream out of the table, and only that one may give its state slot
-        // back (two finishes on one id, or a finish racing an abort, would otherwise release it twice and
-        // two later streams would share one state / digest slot)
-        if (release_slot && erased) e->free_slots.push_back(sp->slot);
-        if (sp->has_expect) {
-            auto it = e->inflight.find(sp->expect);
-            if (it != e->inflight.end() && (it->second.expired() || it->second.lock() == sp)) e->inflight.erase(it);
-        }
+        auto it = e->inflight.find(sp->expect);
+        if (it != e->inflight.end() && (it->second.expired() || it->second.lock() == sp)) e->inflight.erase(it);
     }
 }
 

@@ -278,8 +278,9 @@ struct dm_engine {
     std::unordered_map<uint64_t, std::shared_ptr<Stream>> streams[kStripes];
     std::atomic<uint64_t> n_streams{0};
     std::atomic<bool> ring_starved{false};
-    std::vector<uint32_t> free_slots;
-    uint64_t next_id = 1;
+    std::mutex slot_mu;              // state / digest slots: a lock of their own, so that opening and closing tiny bodies from
+    std::vector<uint32_t> free_slots;                // many threads does not queue on the index lock `mu`
+    std::atomic<uint64_t> next_id{1};
     std::unordered_map<Digest, std::shared_ptr<Blob>, DigestHash> blobs;
     std::unordered_map<Digest, std::weak_ptr<Stream>, DigestHash> inflight;   // open streams by expected digest
     std::mutex reader_mu[kStripes];
