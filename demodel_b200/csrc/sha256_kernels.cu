@@ -467,6 +467,110 @@ sha256_deep_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *_
 }
 
 // ---------------------------------------------------------------------------
+// deep2: two warps per stream - a schedule warp runs ahead of the round warp
+// ---------------------------------------------------------------------------
+// With at most 296 live streams (half the sub-partitions) every stream can have TWO warps, each on a sub-partition
+// of its own.  The serial chain stays what it is - 64 dependent rounds per block on one warp - but everything else
+// leaves that warp: warp 1 loads the next 32 blocks, stores the fused CAS copy and expands the 32 message
+// schedules into the other half of a double-buffered W+K stage while warp 0 is still running the rounds of the
+// current 32.  Hand-over by named barriers (FULL / EMPTY per buffer: one side arrives, the other waits); the round
+// warp never touches global memory inside the loop.  What it buys is phase 1's share of the deep kernel: ~1 cycle
+// per round of 25.9.
+// (barrier ids as immediates: with a register id ptxas reserves all 16 named barriers for the CTA, and the SM's
+//  barrier pool then limits how many CTAs can be resident)
+template <int kId> __device__ __forceinline__ void named_bar_sync() { asm volatile("barrier.sync %0, 64;" :: "n"(kId) : "memory"); }
+template <int kId> __device__ __forceinline__ void named_bar_arrive() { asm volatile("barrier.arrive %0, 64;" :: "n"(kId) : "memory"); }
+__device__ __forceinline__ void full_sync(uint32_t b) { if (b) named_bar_sync<2>(); else named_bar_sync<1>(); }
+__device__ __forceinline__ void full_arrive(uint32_t b) { if (b) named_bar_arrive<2>(); else named_bar_arrive<1>(); }
+__device__ __forceinline__ void empty_sync(uint32_t b) { if (b) named_bar_sync<4>(); else named_bar_sync<3>(); }
+__device__ __forceinline__ void empty_arrive(uint32_t b) { if (b) named_bar_arrive<4>(); else named_bar_arrive<3>(); }
+
+template <int kFma>
+__global__ void __launch_bounds__(64)
+sha256_deep2_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *__restrict__ states,
+                    uint32_t *__restrict__ digests, FmaK k)
+{
+    __shared__ __align__(16) uint32_t kw_smem[2][32 * kKwStride];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t role = threadIdx.x >> 5;          // 0: rounds, 1: loads + schedules
+    const uint32_t j = blockIdx.x;
+    if (j >= njobs) return;
+    const HashJob jb = load_job(jobs, j);
+    const uint64_t nblk = jb.nbytes >> 6;
+    const uint64_t ngroups = (nblk + 31) >> 5;
+    const bool copy = jb.dst != nullptr;
+
+    if (role == 1) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(jb.src) + 4ull * lane;
+        uint4 *q = reinterpret_cast<uint4 *>(jb.dst) + 4ull * lane;
+        uint4 x[4];
+        if (lane < nblk) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = ld_stream(p + i);
+        }
+#pragma unroll 1
+        for (uint64_t g = 0; g < ngroups; ++g) {
+            const uint64_t left = nblk - (g << 5);
+            const uint32_t nv = left < 32 ? (uint32_t)left : 32u;
+            const uint32_t b = (uint32_t)g & 1u;
+            empty_sync(b);                                                // the round warp is done with this buffer
+            if (lane < nv) {
+                if (copy) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) st_stream(q + i, x[i]);
+                }
+                uint32_t w[16];
+                unpack_be(w, x[0], x[1], x[2], x[3]);
+                expand_schedule(w, reinterpret_cast<uint4 *>(kw_smem[b] + lane * kKwStride));
+            }
+            p += 128; q += 128;
+            if (g + 1 < ngroups && lane < left - 32) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) x[i] = ld_stream(p + i);
+            }
+            __threadfence_block();                                        // the stage is written before it is announced
+            full_arrive(b);
+        }
+        return;
+    }
+
+    uint32_t s[8];
+    load_state(s, states, jb.slot, jb.flags);
+    empty_arrive(0);                                                      // both buffers start empty
+    empty_arrive(1);
+#pragma unroll 1
+    for (uint64_t g = 0; g < ngroups; ++g) {
+        const uint64_t left = nblk - (g << 5);
+        const uint32_t nv = left < 32 ? (uint32_t)left : 32u;
+        const uint32_t b = (uint32_t)g & 1u;
+        full_sync(b);
+        const uint32_t *kw = kw_smem[b];
+#pragma unroll 1
+        for (uint32_t blk = 0; blk < nv; ++blk) {
+            const uint4 *kp = reinterpret_cast<const uint4 *>(kw + blk * kKwStride);
+            uint32_t v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = s[i];
+            sha_rounds4<kFma, 0>(v, kp[0], k);   sha_rounds4<kFma, 4>(v, kp[1], k);
+            sha_rounds4<kFma, 8>(v, kp[2], k);   sha_rounds4<kFma, 12>(v, kp[3], k);
+            sha_rounds4<kFma, 16>(v, kp[4], k);  sha_rounds4<kFma, 20>(v, kp[5], k);
+            sha_rounds4<kFma, 24>(v, kp[6], k);  sha_rounds4<kFma, 28>(v, kp[7], k);
+            sha_rounds4<kFma, 32>(v, kp[8], k);  sha_rounds4<kFma, 36>(v, kp[9], k);
+            sha_rounds4<kFma, 40>(v, kp[10], k); sha_rounds4<kFma, 44>(v, kp[11], k);
+            sha_rounds4<kFma, 48>(v, kp[12], k); sha_rounds4<kFma, 52>(v, kp[13], k);
+            sha_rounds4<kFma, 56>(v, kp[14], k); sha_rounds4<kFma, 60>(v, kp[15], k);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] += v[i];
+        }
+        if (g + 2 < ngroups) empty_arrive(b);                             // (nobody waits for the last two)
+    }
+    const uint64_t done = nblk << 6;
+    hash_tail<kFma>(s, jb.src + done, copy ? jb.dst + done : nullptr, (uint32_t)(jb.nbytes & 63u),
+                    (jb.flags & JOB_FINAL) != 0, jb.total_len, lane == 0, k);
+    if (lane == 0) store_state(s, states, digests, jb.slot, jb.flags);
+}
+
+// ---------------------------------------------------------------------------
 // group: S streams per warp (S = 2, 4, 8, 16), between deep (S = 1) and wide (S = 32)
 // ---------------------------------------------------------------------------
 // Same two phases as the deep kernel, with the warp's 32 lanes split as
@@ -653,6 +757,7 @@ cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *st
     if (njobs == 0) return cudaSuccess;
     const uint32_t grid = (njobs + kDeepWarps - 1) / kDeepWarps;
     clear_stale_error();
+    if (variant == 8 && njobs > 296) variant = 7;      // two warps per stream only while each still gets a sub-partition of its own
     switch (variant) {
     case 1: case 3: sha256_deep_kernel<1><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     case 2: sha256_deep_kernel<2><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
@@ -660,6 +765,9 @@ cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *st
     case 5: sha256_deep_kernel<5><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     case 6: sha256_deep_kernel<6><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     case 7: sha256_deep_kernel<7><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    // 8: form 7 with a schedule warp running ahead of the round warp (two warps per stream; callers keep it to
+    //    launches of at most 296 jobs, so that every warp has a sub-partition of its own)
+    case 8: sha256_deep2_kernel<7><<<njobs, 64, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     default: sha256_deep_kernel<0><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     }
     return cudaGetLastError();
@@ -691,7 +799,7 @@ cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *s
     case 4: return launch_group_t<4>(jobs, njobs, states, digests, stream, streams_per_warp);
     case 5: return launch_group_t<5>(jobs, njobs, states, digests, stream, streams_per_warp);
     case 6: return launch_group_t<6>(jobs, njobs, states, digests, stream, streams_per_warp);
-    case 7: return launch_group_t<7>(jobs, njobs, states, digests, stream, streams_per_warp);
+    case 7: case 8: return launch_group_t<7>(jobs, njobs, states, digests, stream, streams_per_warp);
     default: return launch_group_t<0>(jobs, njobs, states, digests, stream, streams_per_warp);
     }
 }

@@ -58,9 +58,11 @@ inline int streams_per_warp_for(uint32_t njobs)
         if ((njobs + s - 1) / s <= kSubPartitions) return s;
     return 32;
 }
-// 7 = short-chain round with e' on the FMA pipe and a' as one IADD3 (sha256_round.cuh): measured on B200
+// Round form 7 = short-chain round with e' on the FMA pipe and a' as one IADD3 (sha256_round.cuh): measured on B200,
 // 256 x 8 MiB: variant 0 132.2 ms, 4 120.6, 5 119.1, 6 119.5, 7 110.7 (profiles/r02_round_variants.txt).
-constexpr int kDefaultDeepVariant = 7;
+// 8 = form 7 with TWO warps per stream while there are at most 296 jobs in the launch (a schedule warp runs ahead of
+// the round warp, sha256_deep2_kernel): 105.4 ms; larger launches fall back to 7 by themselves.
+constexpr int kDefaultDeepVariant = 8;
 
 
 cudaError_t launch_synth_fill(uint64_t seed, uint64_t blob, uint64_t byte_off, void *dst,
