@@ -298,7 +298,11 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": args.workload, "blobs": len(sizes), "bytes_per_step": total,
+        # same key names as the GPU arm's config for what the two arms share
+        "config": {"workload": args.workload, "baseline_config": WORKLOADS[args.workload]["baseline_config"],
+                   "blobs_per_gpu": len(WORKLOADS[args.workload]["sizes"]), "bytes_per_gpu_per_step": sum(WORKLOADS[args.workload]["sizes"]),
+                   "sampled_blobs": len(sizes), "sampled_bytes_per_step": total, "seed": hex(SEED),
+                   "mode": "hash-and-cache (32 KiB EVP_DigestUpdate + memcpy into an in-memory cache)",
                    "note": "OpenSSL EVP_sha256 stand-in for Go crypto/sha256 (no Go toolchain; reference has no such loop)"},
         "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -688,6 +688,8 @@ static int stream_suspend_impl(dm_engine *e, uint64_t id, uint64_t *resume_from)
     if (!ok) {
         unlink((base + ".part.tmp").c_str());
         unlink((base + ".ckpt.tmp").c_str());
+        struct stat st;
+        if (!fresh && stat((base + ".ckpt").c_str(), &st) != 0 && e->n_suspended) e->n_suspended--;    // the older record went with the attempt
         return fail(DM_EIO, "could not save the checkpoint under <cas_dir>/partial (the stream is still open)");
     }
     if (fresh) e->n_suspended++;
