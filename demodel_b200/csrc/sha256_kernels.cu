@@ -668,6 +668,108 @@ sha256_group_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *
     }
 }
 
+// group2: the group kernel with the deep2 split - warp 1 loads, copies out and expands the next group's 32 blocks
+// (lane = block_slot * S + stream, as in the group kernel) while warp 0 runs the current group's 32 / S block-steps for
+// its S streams.  In the group kernel phase 1 is not a 4 % matter as in the deep kernel: per group of 32 blocks it
+// costs ~1500 cycles against (32 / S) x ~1600 for the rounds - 19 % of the time at S = 8, 32 % at S = 16.
+template <int kFma, int S>
+__global__ void __launch_bounds__(64)
+sha256_group2_kernel(const HashJob *__restrict__ jobs, uint32_t njobs, uint32_t *__restrict__ states,
+                     uint32_t *__restrict__ digests, FmaK k)
+{
+    constexpr uint32_t B = 32 / S;
+    __shared__ __align__(16) uint32_t kw_smem[2][32 * kKwStride];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t role = threadIdx.x >> 5;                     // 0: rounds, 1: loads + schedules
+    const uint32_t j = lane % S, b = lane / S;
+    const uint32_t job = blockIdx.x * S + j;
+    const bool live = job < njobs;
+    HashJob jb;
+    if (live) jb = load_job(jobs, job);
+    else { jb.src = nullptr; jb.dst = nullptr; jb.nbytes = 0; jb.total_len = 0; jb.slot = 0; jb.flags = JOB_INIT; jb.one = 1; jb.pad_ = 0; }
+    const uint64_t nblk = jb.nbytes >> 6;                       // this lane's stream
+    uint64_t ngroups = (nblk + B - 1) / B;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {                          // warp-wide max (both warps arrive at the same number)
+        const uint64_t other = __shfl_xor_sync(0xffffffffu, ngroups, o);
+        ngroups = other > ngroups ? other : ngroups;
+    }
+    const bool copy = jb.dst != nullptr;
+
+    if (role == 1) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(jb.src) + 4ull * b;
+        uint4 *q = reinterpret_cast<uint4 *>(jb.dst) + 4ull * b;
+        uint4 x[4];
+        if (b < nblk) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = ld_stream(p + i);
+        }
+#pragma unroll 1
+        for (uint64_t g = 0; g < ngroups; ++g) {
+            const uint64_t blk0 = g * B;
+            const uint32_t buf = (uint32_t)g & 1u;
+            empty_sync(buf);
+            if (blk0 + b < nblk) {
+                if (copy) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) st_stream(q + i, x[i]);
+                }
+                uint32_t w[16];
+                unpack_be(w, x[0], x[1], x[2], x[3]);
+                expand_schedule(w, reinterpret_cast<uint4 *>(kw_smem[buf] + lane * kKwStride));
+            }
+            p += 4 * B; q += 4 * B;
+            if (blk0 + B + b < nblk) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) x[i] = ld_stream(p + i);
+            }
+            __threadfence_block();
+            full_arrive(buf);
+        }
+        return;
+    }
+
+    uint32_t s[8];
+    load_state(s, states, jb.slot, live ? jb.flags : JOB_INIT);
+    empty_arrive(0);
+    empty_arrive(1);
+#pragma unroll 1
+    for (uint64_t g = 0; g < ngroups; ++g) {
+        const uint64_t blk0 = g * B;
+        const uint32_t buf = (uint32_t)g & 1u;
+        full_sync(buf);
+        const uint32_t *kw = kw_smem[buf];
+#pragma unroll 1
+        for (uint32_t st = 0; st < B; ++st) {
+            const bool valid = blk0 + st < nblk;
+            if (__ballot_sync(0xffffffffu, valid) == 0u) break;          // no stream has this step
+            const uint4 *kp = reinterpret_cast<const uint4 *>(kw + (st * S + j) * kKwStride);
+            uint32_t v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = s[i];
+            sha_rounds4<kFma, 0>(v, kp[0], k);   sha_rounds4<kFma, 4>(v, kp[1], k);
+            sha_rounds4<kFma, 8>(v, kp[2], k);   sha_rounds4<kFma, 12>(v, kp[3], k);
+            sha_rounds4<kFma, 16>(v, kp[4], k);  sha_rounds4<kFma, 20>(v, kp[5], k);
+            sha_rounds4<kFma, 24>(v, kp[6], k);  sha_rounds4<kFma, 28>(v, kp[7], k);
+            sha_rounds4<kFma, 32>(v, kp[8], k);  sha_rounds4<kFma, 36>(v, kp[9], k);
+            sha_rounds4<kFma, 40>(v, kp[10], k); sha_rounds4<kFma, 44>(v, kp[11], k);
+            sha_rounds4<kFma, 48>(v, kp[12], k); sha_rounds4<kFma, 52>(v, kp[13], k);
+            sha_rounds4<kFma, 56>(v, kp[14], k); sha_rounds4<kFma, 60>(v, kp[15], k);
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s[i] += v[i];
+            }
+        }
+        if (g + 2 < ngroups) empty_arrive(buf);
+    }
+    if (live) {
+        const uint64_t done = nblk << 6;
+        hash_tail<kFma>(s, jb.src + done, copy ? jb.dst + done : nullptr, (uint32_t)(jb.nbytes & 63u),
+                        (jb.flags & JOB_FINAL) != 0, jb.total_len, b == 0, k);
+        if (b == 0) store_state(s, states, digests, jb.slot, jb.flags);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // synthetic blob bytes
 // ---------------------------------------------------------------------------
@@ -757,6 +859,7 @@ cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *st
     if (njobs == 0) return cudaSuccess;
     const uint32_t grid = (njobs + kDeepWarps - 1) / kDeepWarps;
     clear_stale_error();
+    if (variant == 9) variant = 8;                     // (9 = two-warp group kernels too; the deep kernel's own rule is 8's)
     if (variant == 8 && njobs > 296) variant = 7;      // two warps per stream only while each still gets a sub-partition of its own
     switch (variant) {
     case 1: case 3: sha256_deep_kernel<1><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
@@ -774,6 +877,22 @@ cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *st
 }
 
 // streams_per_warp in {2, 4, 8, 16}; variant 4 = the short-chain round (see sha256_round.cuh), else ptxas' own
+template <int kFma>
+static cudaError_t launch_group2_t(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests,
+                                   cudaStream_t stream, int streams_per_warp)
+{
+    const uint32_t spw = (uint32_t)streams_per_warp;
+    const uint32_t grid = (njobs + spw - 1) / spw;
+    switch (streams_per_warp) {
+    case 2: sha256_group2_kernel<kFma, 2><<<grid, 64, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 4: sha256_group2_kernel<kFma, 4><<<grid, 64, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 8: sha256_group2_kernel<kFma, 8><<<grid, 64, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    case 16: sha256_group2_kernel<kFma, 16><<<grid, 64, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 template <int kFma>
 static cudaError_t launch_group_t(const HashJob *jobs, uint32_t njobs, uint32_t *states, uint32_t *digests,
                                   cudaStream_t stream, int streams_per_warp)
@@ -800,6 +919,7 @@ cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *s
     case 5: return launch_group_t<5>(jobs, njobs, states, digests, stream, streams_per_warp);
     case 6: return launch_group_t<6>(jobs, njobs, states, digests, stream, streams_per_warp);
     case 7: case 8: return launch_group_t<7>(jobs, njobs, states, digests, stream, streams_per_warp);
+    case 9: return launch_group2_t<7>(jobs, njobs, states, digests, stream, streams_per_warp);      // two warps per group of S streams
     default: return launch_group_t<0>(jobs, njobs, states, digests, stream, streams_per_warp);
     }
 }
