@@ -92,8 +92,8 @@ def _cfs_throttle():
 
 def _kernel_for(n):
     """Mirror of streams_per_warp_for() in demodel_b200/csrc/sha256_kernels.cuh (for the report only)."""
-    for limit, name in ((592, "deep (1 stream/warp)"), (1184, "group (2 streams/warp)"), (2368, "group (4 streams/warp)"),
-                        (4736, "group (8 streams/warp)"), (9472, "group (16 streams/warp)")):
+    for limit, name in ((296, "deep (1 stream/warp pair)"), (592, "group (2 streams/warp pair)"), (1184, "group (4 streams/warp pair)"),
+                        (2368, "group (8 streams/warp pair)"), (4736, "group (16 streams/warp pair)"), (9472, "group (16 streams/warp)")):
         if n <= limit:
             return name
     return "wide (32 streams/warp)"

@@ -201,7 +201,7 @@ static int engine_create(const dm_config *cfg, dm_engine **out)
         int w = -1, d = -1;
         if (sscanf(v, "%d,%d", &w, &d) >= 1) {
             if (w >= 0 && w < 24) e->variant_wide = w;
-            if (d >= 0 && d <= 9) e->variant_deep = d;   // 4..7 = short-chain rounds (deep and group kernels)
+            if (d >= 0 && d <= 10) e->variant_deep = d;   // 4..7 = short-chain rounds (deep and group kernels)
         }
     }
     // Streaming stores for the socket -> ring copy from 16 KiB pieces up (io.Copy moves 32 KiB); DM_NT_COPY_MIN=0

@@ -530,11 +530,15 @@ static int ingest_device_impl(dm_engine *e, const void *dev_base, const uint64_t
     const bool forced = e->force_spw || (flags & (DM_ING_FORCE_WIDE | DM_ING_FORCE_DEEP | DM_ING_SPW_MASK));
     if (spw > 1 && !forced && n > 1) {
         const uint64_t longest = e->ing_jobs_h[0].nbytes;           // jobs are sorted longest first here
-        while (n_long < n && n_long < 592 && e->ing_jobs_h[n_long].nbytes * 4 >= longest) ++n_long;
-        if (n_long == n || longest < e->split_min) n_long = 0;      // not skewed, or nothing long enough to matter
+        while (n_long < n && n_long < dm::kSubPartitions && e->ing_jobs_h[n_long].nbytes * 4 >= longest) ++n_long;
+        // not skewed (everything is "long", or more long jobs than sub-partitions), or nothing long enough to matter
+        if (n_long == n || longest < e->split_min || e->ing_jobs_h[n_long].nbytes * 4 >= longest) n_long = 0;
     }
     const uint32_t n_rest = n - n_long;
-    const int spw_rest = n_long ? dm::streams_per_warp_for(n_rest) : spw;
+    // the two launches of a split batch share the chip: the rest runs one warp per group (the long jobs keep their
+    // warp pairs while there are at most 296 of them)
+    const int spw_rest = n_long ? dm::streams_per_warp_unpaired(n_rest) : spw;
+    const int v_rest = n_long && e->variant_deep >= 8 ? 7 : e->variant_deep;
     cudaStream_t st = e->ingest_stream, st2 = e->util_stream;
     (void)cudaGetLastError();           // the caller's thread may carry a stale "not ready" from its own event polling
     cudaError_t err = cudaMemcpyAsync(e->ing_jobs_d, e->ing_jobs_h, sizeof(dm::HashJob) * (uint64_t)n, cudaMemcpyHostToDevice, st);
@@ -546,9 +550,9 @@ static int ingest_device_impl(dm_engine *e, const void *dev_base, const uint64_t
     }
     if (err == cudaSuccess) {
         const dm::HashJob *rest = e->ing_jobs_d + n_long;
-        err = spw_rest == 1 ? dm::launch_sha256_deep(rest, n_rest, e->ing_states, e->ing_digests, st, e->variant_deep)
+        err = spw_rest == 1 ? dm::launch_sha256_deep(rest, n_rest, e->ing_states, e->ing_digests, st, v_rest)
             : spw_rest == 32 ? dm::launch_sha256_wide(rest, n_rest, e->ing_states, e->ing_digests, st, e->variant_wide)
-                             : dm::launch_sha256_group(rest, n_rest, e->ing_states, e->ing_digests, st, spw_rest, e->variant_deep);
+                             : dm::launch_sha256_group(rest, n_rest, e->ing_states, e->ing_digests, st, spw_rest, v_rest);
     }
     if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev1, st);
     if (err == cudaSuccess && n_long) err = cudaStreamWaitEvent(st, e->ing_ev2, 0);       // digests of both launches

@@ -860,7 +860,8 @@ cudaError_t launch_sha256_deep(const HashJob *jobs, uint32_t njobs, uint32_t *st
     const uint32_t grid = (njobs + kDeepWarps - 1) / kDeepWarps;
     clear_stale_error();
     if (variant == 9) variant = 8;                     // (9 = two-warp group kernels too; the deep kernel's own rule is 8's)
-    if (variant == 8 && njobs > 296) variant = 7;      // two warps per stream only while each still gets a sub-partition of its own
+    if (variant == 8 && njobs > kMaxWarpPairs) variant = 7;
+    if (variant == 10) variant = 8;                    // 10 = two warps per stream whatever the count (A/B of the 296 rule)      // two warps per stream only while each still gets a sub-partition of its own
     switch (variant) {
     case 1: case 3: sha256_deep_kernel<1><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
     case 2: sha256_deep_kernel<2><<<grid, 32 * kDeepWarps, 0, stream>>>(jobs, njobs, states, digests, kFmaK); break;
@@ -918,8 +919,11 @@ cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *s
     case 4: return launch_group_t<4>(jobs, njobs, states, digests, stream, streams_per_warp);
     case 5: return launch_group_t<5>(jobs, njobs, states, digests, stream, streams_per_warp);
     case 6: return launch_group_t<6>(jobs, njobs, states, digests, stream, streams_per_warp);
-    case 7: case 8: return launch_group_t<7>(jobs, njobs, states, digests, stream, streams_per_warp);
-    case 9: return launch_group2_t<7>(jobs, njobs, states, digests, stream, streams_per_warp);      // two warps per group of S streams
+    case 7: case 8: case 10: return launch_group_t<7>(jobs, njobs, states, digests, stream, streams_per_warp);
+    case 9:                                             // two warps per group of S streams, while every pair can have two sub-partitions
+        if ((njobs + (uint32_t)streams_per_warp - 1) / (uint32_t)streams_per_warp <= kMaxWarpPairs)
+            return launch_group2_t<7>(jobs, njobs, states, digests, stream, streams_per_warp);
+        return launch_group_t<7>(jobs, njobs, states, digests, stream, streams_per_warp);
     default: return launch_group_t<0>(jobs, njobs, states, digests, stream, streams_per_warp);
     }
 }

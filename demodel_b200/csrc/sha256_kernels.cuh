@@ -46,23 +46,41 @@ cudaError_t launch_sha256_group(const HashJob *jobs, uint32_t njobs, uint32_t *s
 
 // Kernel choice by live-stream count: aim for one to two warps on
 // each of the 592 sub-partitions.  Returns streams per warp: 1 = deep, 32 = wide.
+constexpr uint32_t kSubPartitions = 592;             // 148 SMs x 4
+constexpr uint32_t kMaxWarpPairs = kSubPartitions / 2;
+
 inline int streams_per_warp_for(uint32_t njobs)
 {
-    // One warp per sub-partition (148 SMs x 4) for as long as that is possible: the smallest S whose njobs / S warps
-    // still fit one per sub-partition; past 16 streams per warp, a lane per stream.  Measured on B200 with the
-    // variant-7 round (tools/ab_group.sh, profiles/r02_streams_per_warp_sweep.txt): a second warp on a sub-partition
-    // halves both (640 streams, one warp each: 340 ms; two per warp: 206 ms), and every crossover sits where the
-    // warp count passes 592.
-    constexpr uint32_t kSubPartitions = 592;
+    // Measured on B200 (profiles/r02_streams_per_warp_sweep.txt): a warp must never share its sub-partition with
+    // another round warp (640 streams, one warp each: 340 ms; two per warp: 206 ms), and while there are sub-partitions
+    // to spare a SECOND warp per group - loading and expanding the next blocks' schedules ahead of the round warp -
+    // is worth far more than a smaller S (4096 streams: 16 per warp, paired: 30.7 ms; 16 per warp, alone: 41.8 ms).
+    // So: the smallest S in {1, 2, 4, 8, 16} whose njobs / S groups can each have a warp PAIR (<= 296 groups, up to
+    // 4736 streams); then 16 per warp, one warp per sub-partition (<= 9472 streams); then a lane per stream.
+    for (int s = 1; s <= 16; s *= 2)
+        if ((njobs + s - 1) / s <= kMaxWarpPairs) return s;
+    if ((njobs + 15) / 16 <= kSubPartitions) return 16;
+    return 32;
+}
+// One warp per group, no pairs: the smallest S that still leaves every warp a sub-partition (the rule for a launch
+// that shares the chip with another one, engine_cache.cu's split batches).
+inline int streams_per_warp_unpaired(uint32_t njobs)
+{
     for (int s = 1; s <= 16; s *= 2)
         if ((njobs + s - 1) / s <= kSubPartitions) return s;
     return 32;
 }
+// Can a launch of njobs jobs at S streams per warp run as warp pairs, given that `resident` jobs (this launch and the
+// ones still running, all at S per warp) share the chip?
+inline bool warp_pairs_fit(uint32_t resident, int s) { return s <= 16 && (resident + (uint32_t)s - 1) / (uint32_t)s <= kMaxWarpPairs; }
+
 // Round form 7 = short-chain round with e' on the FMA pipe and a' as one IADD3 (sha256_round.cuh): measured on B200,
 // 256 x 8 MiB: variant 0 132.2 ms, 4 120.6, 5 119.1, 6 119.5, 7 110.7 (profiles/r02_round_variants.txt).
 // 8 = form 7 with TWO warps per stream while there are at most 296 jobs in the launch (a schedule warp runs ahead of
 // the round warp, sha256_deep2_kernel): 105.4 ms; larger launches fall back to 7 by themselves.
-constexpr int kDefaultDeepVariant = 8;
+// 9 = 8 plus the same split in the S-streams-per-warp kernels (sha256_group2_kernel) while the launch has at most 296
+// groups: 4096 streams 41.8 -> 30.7 ms, 2048 streams 75.5 -> 57.2 ms, 1024 streams 129.2 -> 111.0 ms.
+constexpr int kDefaultDeepVariant = 9;
 
 
 cudaError_t launch_synth_fill(uint64_t seed, uint64_t blob, uint64_t byte_off, void *dst,

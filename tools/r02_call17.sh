@@ -15,4 +15,6 @@ run 21,8 1024 2; run 21,9 1024 2; run 21,9 1024 4
 run 21,8 2048 4; run 21,9 2048 4; run 21,9 2048 8
 run 21,8 4096 16; run 21,9 4096 8; run 21,9 4096 16
 run 21,8 8192 16; run 21,9 8192 16
+run 21,8 512 1; run 21,10 512 1; run 21,9 512 2
+run 21,8 592 1; run 21,10 592 1; run 21,9 592 2
 } > gpurun_out/r02_group2_sweep.txt 2>&1
