@@ -161,6 +161,11 @@ void dm_engine_destroy(dm_engine *e)
     if (e->ing_ev0) cudaEventDestroy(e->ing_ev0);
     if (e->ing_ev1) cudaEventDestroy(e->ing_ev1);
     if (e->ing_ev2) cudaEventDestroy(e->ing_ev2);
+    for (int i = 0; i < kIngestMaxChunks; ++i) {
+        if (e->ing_cev_k[i]) cudaEventDestroy(e->ing_cev_k[i]);
+        if (e->ing_cev_done[i]) cudaEventDestroy(e->ing_cev_done[i]);
+        if (e->ing_streams[i]) cudaStreamDestroy(e->ing_streams[i]);
+    }
     if (e->pack_dev_base) cudaFree(e->pack_dev_base);
     if (e->d_states) cudaFree(e->d_states);
     if (e->h_digests) cudaFreeHost(e->h_digests);
@@ -208,6 +213,7 @@ static int engine_create(const dm_config *cfg, dm_engine **out)
     // turns them off, any other value moves the threshold (A/B runs).
     e->nt_copy_min = 16384;
     if (const char *v = getenv("DM_NT_COPY_MIN")) e->nt_copy_min = (uint32_t)strtoul(v, nullptr, 10);
+    if (const char *v = getenv("DM_INGEST_CHUNKS")) e->ingest_chunks = (uint32_t)std::min<long>(std::max<long>(atol(v), 0), kIngestMaxChunks);   // tuning / tests only
     if (const char *v = getenv("DM_SPLIT_MIN_BYTES")) e->split_min = strtoull(v, nullptr, 10);       // tuning / tests only
     if (!e->cfg.slab_bytes) e->cfg.slab_bytes = 1u << 20;
     if (!e->cfg.ring_bytes) e->cfg.ring_bytes = 256ull << 20;
@@ -248,6 +254,11 @@ static int engine_create(const dm_config *cfg, dm_engine **out)
     CU_INIT(cudaEventCreate(&e->ing_ev0));
     CU_INIT(cudaEventCreate(&e->ing_ev1));
     CU_INIT(cudaEventCreate(&e->ing_ev2));
+    for (int i = 0; i < kIngestMaxChunks; ++i) {
+        CU_INIT(cudaStreamCreateWithFlags(&e->ing_streams[i], cudaStreamNonBlocking));
+        CU_INIT(cudaEventCreate(&e->ing_cev_k[i]));
+        CU_INIT(cudaEventCreateWithFlags(&e->ing_cev_done[i], cudaEventDisableTiming));
+    }
 
     if ((e->cfg.flags & DM_F_NO_HBM_CAS) && !e->cfg.hbm_cas_bytes) e->cfg.hbm_cas_bytes = 1u << 20;   // only dm_ingest_device would use it
     if (!e->cfg.hbm_cas_bytes) {

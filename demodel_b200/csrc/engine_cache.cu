@@ -459,6 +459,133 @@ int dm_cache_alias_get(dm_engine *e, const char *key, uint8_t digest_out[32])
 
 // ---- device-resident ingest -------------------------------------------------------
 
+namespace {
+
+// One dm_ingest_device call.  Jobs are addressed by POSITION p in launch order (longest first when the kernel shape
+// wants that); caller_index(p) is the blob the caller knows.  HashJob::slot = p, so a chunk's digests are contiguous.
+struct IngestBatch {
+    dm_engine *e;
+    const uint8_t *base;
+    const uint64_t *offsets, *lengths;
+    const uint8_t *expect;
+    uint8_t *digests_out, *matched_out;
+    bool hash_only, replace;
+    const uint32_t *order = nullptr;         // position -> caller index; nullptr = identity
+    std::vector<Extent> ext;                 // by position: where the blob's CAS copy goes
+    std::vector<std::shared_ptr<Blob>> parked;   // by position: the cached copy whose extent is being rewritten (REPLACE)
+    uint32_t published = 0;                  // positions from here on may hold an extent or a parked blob nothing else knows about
+    uint32_t caller_index(uint32_t p) const { return order ? order[p] : p; }
+};
+
+// Before the launch of positions [lo, hi): extents and the job table.
+int ingest_prepare(IngestBatch &B, uint32_t lo, uint32_t hi)
+{
+    dm_engine *e = B.e;
+    if (!B.hash_only) {
+        std::vector<Extent> freed;
+        if (B.replace && B.expect) {
+            // The previous copy of a blob we are about to re-ingest goes out of sight, and - when its one extent has
+            // the right size - that extent is simply written again: no arena traffic, no new index entry, and the
+            // blob comes back by pointer (unpark_many).  Anything else is evicted the ordinary way.
+            std::lock_guard<std::mutex> g(e->mu);
+            auto digest_at = [&](uint32_t p) { Digest d; memcpy(d.b, B.expect + 32ull * B.caller_index(p), 32); return d; };
+            constexpr uint32_t kAhead = 16;                          // the index slot of a digest is known from the digest alone
+            for (uint32_t p = lo; p < hi; ++p) {
+                if (p + kAhead < hi) e->blobs.prefetch(digest_at(p + kAhead));
+                const uint32_t i = B.caller_index(p);
+                const Digest d = digest_at(p);
+                auto it = e->blobs.find(d);
+                if (it == e->blobs.end() || !it->second->in_hbm || it->second->readers) continue;
+                Blob *b = it->second.get();
+                const uint64_t want = round_up(std::max<uint64_t>(B.lengths[i], 1), kAlign);
+                const bool disk_safe = e->cas_dir.empty() || (b->on_disk && b->spill_done);
+                b->in_hbm = false;
+                lru_drop(e, b);
+                if (disk_safe && b->extents.size() == 1 && b->extents[0].len == want) {
+                    B.ext[p] = b->extents[0];
+                    b->extents.clear();
+                    B.parked[p] = it->second;
+                } else {
+                    freed.insert(freed.end(), b->extents.begin(), b->extents.end());
+                    b->extents.clear();                              // under the lock (see evict_for)
+                    if (!b->on_disk) e->blobs.erase(it);
+                }
+            }
+        }
+        uint32_t p = lo;
+        {                                                            // all extents of the chunk under one arena lock
+            std::lock_guard<std::mutex> g(e->arena_mu);
+            for (const Extent &x : freed) e->arena.release(x.off, x.len);
+            for (; p < hi; ++p) {
+                if (B.parked[p]) continue;
+                const uint64_t want = round_up(std::max<uint64_t>(B.lengths[B.caller_index(p)], 1), kAlign);
+                uint64_t off;
+                if (!e->arena.alloc(want, &off)) break;
+                B.ext[p] = Extent{off, want};
+            }
+        }
+        for (; p < hi; ++p) {                                        // arena full: evict LRU blobs one allocation at a time
+            if (!B.parked[p]) {
+                Extent x;
+                if (!arena_alloc(e, B.lengths[B.caller_index(p)], &x)) return fail(DM_ENOMEM, "HBM CAS arena exhausted");
+                B.ext[p] = x;
+            }
+        }
+    }
+    for (uint32_t p = lo; p < hi; ++p) {
+        const uint32_t i = B.caller_index(p);
+        dm::HashJob &jb = e->ing_jobs_h[p];
+        jb.src = B.base + B.offsets[i]; jb.dst = B.hash_only ? nullptr : e->arena_base + B.ext[p].off;
+        jb.nbytes = B.lengths[i]; jb.total_len = B.lengths[i];
+        jb.slot = p; jb.flags = dm::JOB_INIT | dm::JOB_FINAL; jb.one = 1; jb.pad_ = 0;
+    }
+    return DM_OK;
+}
+
+// After the digests of positions [lo, hi) are back: verdicts out, verified copies published, the others released.
+void ingest_publish(IngestBatch &B, uint32_t lo, uint32_t hi)
+{
+    dm_engine *e = B.e;
+    std::vector<Verified> good;
+    std::vector<Parked> back, gone;
+    std::vector<Extent> bad;
+    if (!B.hash_only) { good.reserve(hi - lo); if (B.replace) back.reserve(hi - lo); }
+    for (uint32_t p = lo; p < hi; ++p) {
+        const uint32_t i = B.caller_index(p);
+        Digest d;
+        words_to_digest(e->ing_digests_h + 8ull * p, d.b);
+        if (B.digests_out) memcpy(B.digests_out + 32ull * i, d.b, 32);
+        const int ok = (!B.expect || memcmp(B.expect + 32ull * i, d.b, 32) == 0) ? 1 : 0;
+        if (B.matched_out) B.matched_out[i] = (uint8_t)ok;
+        if (B.hash_only) continue;
+        if (!ok) e->st_mismatch++;
+        if (B.parked[p]) (ok ? back : gone).push_back(Parked{std::move(B.parked[p]), B.ext[p]});   // parked under expect[i]: ok means it IS that blob
+        else if (ok) good.push_back(Verified{d, B.lengths[i], B.ext[p]});
+        else bad.push_back(B.ext[p]);
+    }
+    B.published = hi;
+    if (!good.empty()) publish_many(e, good);
+    if (!back.empty() || !gone.empty()) unpark_many(e, back, gone);
+    if (!bad.empty()) free_extents(e, bad);
+}
+
+// A failed call: whatever was prepared and not yet published goes back (the caller has synchronised the streams).
+void ingest_unwind(IngestBatch &B)
+{
+    if (B.hash_only) return;
+    std::vector<Parked> none, gone;
+    std::vector<Extent> ext;
+    for (uint32_t p = B.published; p < B.ext.size(); ++p) {
+        if (B.parked[p]) gone.push_back(Parked{std::move(B.parked[p]), B.ext[p]});
+        else if (B.ext[p].len) ext.push_back(B.ext[p]);              // allocated extents are never empty
+        B.ext[p] = Extent{0, 0};
+    }
+    if (!gone.empty()) unpark_many(B.e, none, gone);
+    if (!ext.empty()) free_extents(B.e, ext);
+}
+
+}  // namespace
+
 static int ingest_device_impl(dm_engine *e, const void *dev_base, const uint64_t *offsets, const uint64_t *lengths,
                               uint32_t n, const uint8_t *expect, uint8_t *digests_out, uint8_t *matched_out,
                               uint32_t flags, double *kernel_ms)
@@ -467,59 +594,35 @@ static int ingest_device_impl(dm_engine *e, const void *dev_base, const uint64_t
     if (kernel_ms) *kernel_ms = 0.0;
     if (n == 0) return DM_OK;
     if (((uintptr_t)dev_base) & 15) return fail(DM_EINVAL, "dev_base must be 16-byte aligned");
-    for (uint32_t i = 0; i < n; ++i)
+    uint64_t total = 0;
+    bool sorted = true;                                  // equal-sized batches (the common bulk case) need no reordering
+    for (uint32_t i = 0; i < n; ++i) {
         if (offsets[i] & 15) return fail(DM_EINVAL, "offsets must be multiples of 16");
+        total += lengths[i];
+        if (i && lengths[i - 1] < lengths[i]) sorted = false;
+    }
     cudaSetDevice(e->device);
     std::lock_guard<std::mutex> gi(e->ingest_mu);
     int rc = ensure_ingest_scratch(e, n);
     if (rc != DM_OK) return rc;
-    const bool hash_only = (flags & DM_ING_HASH_ONLY) != 0;
-    std::vector<Extent> ext(hash_only ? 0 : n, Extent{0, 0});
-    auto cleanup = [&] {
-        std::lock_guard<std::mutex> g(e->arena_mu);
-        for (const Extent &x : ext) e->arena.release(x.off, x.len);
-    };
-    if ((flags & DM_ING_REPLACE) && expect && !hash_only) evict_many(e, expect, n);
-    const uint8_t *base = static_cast<const uint8_t *>(dev_base);
-    uint64_t total = 0;
-    uint32_t allocated = 0;
-    if (!hash_only) {                                   // fast path: all extents under one arena lock
-        std::lock_guard<std::mutex> g(e->arena_mu);
-        for (; allocated < n; ++allocated) {
-            const uint64_t want = round_up(std::max<uint64_t>(lengths[allocated], 1), kAlign);
-            uint64_t off;
-            if (!e->arena.alloc(want, &off)) break;
-            ext[allocated] = Extent{off, want};
-        }
-    }
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint64_t len = lengths[i];
-        dm::HashJob &jb = e->ing_jobs_h[i];
-        jb.src = base + offsets[i]; jb.dst = nullptr; jb.nbytes = len; jb.total_len = len;
-        jb.slot = i; jb.flags = dm::JOB_INIT | dm::JOB_FINAL; jb.one = 1; jb.pad_ = 0;
-        if (!hash_only) {
-            if (i >= allocated) {                       // arena full: evict LRU blobs one allocation at a time
-                Extent x;
-                if (!arena_alloc(e, len, &x)) { cleanup(); return fail(DM_ENOMEM, "HBM CAS arena exhausted"); }
-                ext[i] = x;
-            }
-            jb.dst = e->arena_base + ext[i].off;
-        }
-        total += len;
+    IngestBatch B;
+    B.e = e; B.base = static_cast<const uint8_t *>(dev_base); B.offsets = offsets; B.lengths = lengths; B.expect = expect;
+    B.digests_out = digests_out; B.matched_out = matched_out;
+    B.hash_only = (flags & DM_ING_HASH_ONLY) != 0; B.replace = (flags & DM_ING_REPLACE) != 0;
+    if (!B.hash_only) {
+        B.ext.assign(n, Extent{0, 0});
+        B.parked.resize(n);
     }
     int spw = e->force_spw ? e->force_spw : dm::streams_per_warp_for(n);
     if (flags & DM_ING_FORCE_WIDE) spw = 32;
     if (flags & DM_ING_FORCE_DEEP) spw = 1;
     if (flags & DM_ING_SPW_MASK) spw = 1 << (((flags & DM_ING_SPW_MASK) >> DM_ING_SPW_SHIFT) - 1);
-    std::vector<uint32_t> order(n);
-    for (uint32_t i = 0; i < n; ++i) order[i] = i;
-    bool sorted = true;                                  // equal-sized batches (the common bulk case) need no reordering
-    for (uint32_t i = 1; i < n && sorted; ++i) sorted = e->ing_jobs_h[i - 1].nbytes >= e->ing_jobs_h[i].nbytes;
-    if (spw > 1 && !sorted) {
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-            return e->ing_jobs_h[a].nbytes > e->ing_jobs_h[b].nbytes; });
-        std::vector<dm::HashJob> tmp(e->ing_jobs_h, e->ing_jobs_h + n);
-        for (uint32_t i = 0; i < n; ++i) e->ing_jobs_h[i] = tmp[order[i]];   // slot keeps the caller's index
+    std::vector<uint32_t> order;
+    if (spw > 1 && !sorted) {                            // lanes of a warp should end together: longest first
+        order.resize(n);
+        for (uint32_t i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return lengths[a] > lengths[b]; });
+        B.order = order.data();
     }
     // A batch whose sizes are badly skewed (a few multi-GiB layers among thousands of small files) is two batches: the
     // launch lasts as long as its longest chain, and a chain runs fastest with a warp of its own, so the long jobs
@@ -529,71 +632,113 @@ static int ingest_device_impl(dm_engine *e, const void *dev_base, const uint64_t
     uint32_t n_long = 0;
     const bool forced = e->force_spw || (flags & (DM_ING_FORCE_WIDE | DM_ING_FORCE_DEEP | DM_ING_SPW_MASK));
     if (spw > 1 && !forced && n > 1) {
-        const uint64_t longest = e->ing_jobs_h[0].nbytes;           // jobs are sorted longest first here
-        while (n_long < n && n_long < dm::kSubPartitions && e->ing_jobs_h[n_long].nbytes * 4 >= longest) ++n_long;
+        const uint64_t longest = lengths[B.caller_index(0)];        // positions are longest first here
+        while (n_long < n && n_long < dm::kSubPartitions && lengths[B.caller_index(n_long)] * 4 >= longest) ++n_long;
         // not skewed (everything is "long", or more long jobs than sub-partitions), or nothing long enough to matter
-        if (n_long == n || longest < e->split_min || e->ing_jobs_h[n_long].nbytes * 4 >= longest) n_long = 0;
+        if (n_long == n || longest < e->split_min || lengths[B.caller_index(n_long)] * 4 >= longest) n_long = 0;
     }
     const uint32_t n_rest = n - n_long;
     // the two launches of a split batch share the chip: the rest runs one warp per group (the long jobs keep their
     // warp pairs while there are at most 296 of them)
     const int spw_rest = n_long ? dm::streams_per_warp_unpaired(n_rest) : spw;
     const int v_rest = n_long && e->variant_deep >= 8 ? 7 : e->variant_deep;
+    // Very large lane-per-stream batches go out in chunks, each on a stream of its own: at 10^5 blobs the host work
+    // around the launch (extents, index) is of the order of the kernel itself, and this way all but the first
+    // chunk's preparation and the last chunk's publication happens while kernels run.  The launches overlap on the
+    // device (together they are the same CTAs), so the GPU side costs nothing.
+    uint32_t nchunks = 1;
+    if (!n_long && spw_rest == 32) {
+        // (a forced kernel shape is a measurement of that kernel: one launch, unless DM_INGEST_CHUNKS says otherwise)
+        nchunks = e->ingest_chunks ? std::min<uint32_t>(e->ingest_chunks, n) : forced ? 1 : std::min<uint32_t>(kIngestMaxChunks, n / kIngestChunkMin);
+        nchunks = std::max<uint32_t>(1, nchunks);
+    }
     cudaStream_t st = e->ingest_stream, st2 = e->util_stream;
     (void)cudaGetLastError();           // the caller's thread may carry a stale "not ready" from its own event polling
-    cudaError_t err = cudaMemcpyAsync(e->ing_jobs_d, e->ing_jobs_h, sizeof(dm::HashJob) * (uint64_t)n, cudaMemcpyHostToDevice, st);
-    if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev0, st);
-    if (err == cudaSuccess && n_long) {
-        err = cudaStreamWaitEvent(st2, e->ing_ev0, 0);              // the job table is in place
-        if (err == cudaSuccess) err = dm::launch_sha256_deep(e->ing_jobs_d, n_long, e->ing_states, e->ing_digests, st2, e->variant_deep);
-        if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev2, st2);
-    }
-    if (err == cudaSuccess) {
-        const dm::HashJob *rest = e->ing_jobs_d + n_long;
-        err = spw_rest == 1 ? dm::launch_sha256_deep(rest, n_rest, e->ing_states, e->ing_digests, st, v_rest)
-            : spw_rest == 32 ? dm::launch_sha256_wide(rest, n_rest, e->ing_states, e->ing_digests, st, e->variant_wide)
-                             : dm::launch_sha256_group(rest, n_rest, e->ing_states, e->ing_digests, st, spw_rest, v_rest);
-    }
-    if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev1, st);
-    if (err == cudaSuccess && n_long) err = cudaStreamWaitEvent(st, e->ing_ev2, 0);       // digests of both launches
-    if (err == cudaSuccess) err = cudaMemcpyAsync(e->ing_digests_h, e->ing_digests, 32ull * n, cudaMemcpyDeviceToHost, st);
-    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
-    if (err != cudaSuccess) {
-        cudaStreamSynchronize(st);      // whatever was enqueued before the failure still uses the job table and the extents
-        cudaStreamSynchronize(st2);
-        cleanup();
-        return fail_cuda(err, "dm_ingest_device launch");
-    }
+    cudaError_t err = cudaSuccess;
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, e->ing_ev0, e->ing_ev1);
-    if (n_long) {                       // two overlapping launches: the pass lasted until the later one ended
-        float ms2 = 0.f;
-        cudaEventElapsedTime(&ms2, e->ing_ev0, e->ing_ev2);
-        ms = std::max(ms, ms2);
-        e->st_launches++; e->st_deep++;
+    if (nchunks > 1) {
+        uint32_t per = (n + nchunks - 1) / nchunks;
+        if (per >= 64) per = (per + 31) / 32 * 32;                                // whole warps per chunk
+        uint32_t lo_of[kIngestMaxChunks + 1];
+        for (uint32_t c = 0; c <= nchunks; ++c) lo_of[c] = std::min<uint64_t>(n, (uint64_t)c * per);
+        uint32_t launched = 0, reaped = 0;
+        auto reap = [&]() {                                 // digests of the oldest chunk in flight
+            err = cudaEventSynchronize(e->ing_cev_done[reaped]);
+            if (err != cudaSuccess) return;
+            ingest_publish(B, lo_of[reaped], lo_of[reaped + 1]);
+            ++reaped;
+        };
+        while (launched < nchunks && lo_of[launched] < n) {
+            const uint32_t c = launched, lo = lo_of[c], hi = lo_of[c + 1];
+            rc = ingest_prepare(B, lo, hi);
+            if (rc != DM_OK) break;
+            cudaStream_t cs = e->ing_streams[c];
+            err = cudaMemcpyAsync(e->ing_jobs_d + lo, e->ing_jobs_h + lo, sizeof(dm::HashJob) * (uint64_t)(hi - lo), cudaMemcpyHostToDevice, cs);
+            if (err == cudaSuccess && c == 0) err = cudaEventRecord(e->ing_ev0, cs);
+            if (err == cudaSuccess) err = dm::launch_sha256_wide(e->ing_jobs_d + lo, hi - lo, e->ing_states, e->ing_digests, cs, e->variant_wide);
+            if (err == cudaSuccess) err = cudaEventRecord(e->ing_cev_k[c], cs);
+            if (err == cudaSuccess) err = cudaMemcpyAsync(e->ing_digests_h + 8ull * lo, e->ing_digests + 8ull * lo, 32ull * (hi - lo), cudaMemcpyDeviceToHost, cs);
+            if (err == cudaSuccess) err = cudaEventRecord(e->ing_cev_done[c], cs);
+            ++launched;                                     // whatever did get enqueued is waited for, also on failure
+            while (reaped < launched && err == cudaSuccess) {           // publish what has finished meanwhile, without waiting
+                const cudaError_t q = cudaEventQuery(e->ing_cev_done[reaped]);
+                if (q == cudaErrorNotReady) { (void)cudaGetLastError(); break; }     // not an error, but it sticks to the thread
+                if (q != cudaSuccess) { err = q; break; }
+                reap();
+            }
+            if (err != cudaSuccess) break;
+        }
+        while (rc == DM_OK && err == cudaSuccess && reaped < launched) reap();
+        if (rc != DM_OK || err != cudaSuccess) {
+            for (uint32_t c = 0; c < launched; ++c) cudaStreamSynchronize(e->ing_streams[c]);
+            ingest_unwind(B);
+            return rc != DM_OK ? rc : fail_cuda(err, "dm_ingest_device launch");
+        }
+        for (uint32_t c = 0; c < launched; ++c) {           // the pass lasted from the first launch to the last one's end
+            float t = 0.f;
+            cudaEventElapsedTime(&t, e->ing_ev0, e->ing_cev_k[c]);
+            ms = std::max(ms, t);
+        }
+        e->st_launches += launched; e->st_wide += launched;
+    } else {
+        rc = ingest_prepare(B, 0, n);
+        if (rc != DM_OK) { ingest_unwind(B); return rc; }
+        err = cudaMemcpyAsync(e->ing_jobs_d, e->ing_jobs_h, sizeof(dm::HashJob) * (uint64_t)n, cudaMemcpyHostToDevice, st);
+        if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev0, st);
+        if (err == cudaSuccess && n_long) {
+            err = cudaStreamWaitEvent(st2, e->ing_ev0, 0);              // the job table is in place
+            if (err == cudaSuccess) err = dm::launch_sha256_deep(e->ing_jobs_d, n_long, e->ing_states, e->ing_digests, st2, e->variant_deep);
+            if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev2, st2);
+        }
+        if (err == cudaSuccess) {
+            const dm::HashJob *rest = e->ing_jobs_d + n_long;
+            err = spw_rest == 1 ? dm::launch_sha256_deep(rest, n_rest, e->ing_states, e->ing_digests, st, v_rest)
+                : spw_rest == 32 ? dm::launch_sha256_wide(rest, n_rest, e->ing_states, e->ing_digests, st, e->variant_wide)
+                                 : dm::launch_sha256_group(rest, n_rest, e->ing_states, e->ing_digests, st, spw_rest, v_rest);
+        }
+        if (err == cudaSuccess) err = cudaEventRecord(e->ing_ev1, st);
+        if (err == cudaSuccess && n_long) err = cudaStreamWaitEvent(st, e->ing_ev2, 0);       // digests of both launches
+        if (err == cudaSuccess) err = cudaMemcpyAsync(e->ing_digests_h, e->ing_digests, 32ull * n, cudaMemcpyDeviceToHost, st);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+        if (err != cudaSuccess) {
+            cudaStreamSynchronize(st);      // whatever was enqueued before the failure still uses the job table and the extents
+            cudaStreamSynchronize(st2);
+            ingest_unwind(B);
+            return fail_cuda(err, "dm_ingest_device launch");
+        }
+        cudaEventElapsedTime(&ms, e->ing_ev0, e->ing_ev1);
+        if (n_long) {                       // two overlapping launches: the pass lasted until the later one ended
+            float ms2 = 0.f;
+            cudaEventElapsedTime(&ms2, e->ing_ev0, e->ing_ev2);
+            ms = std::max(ms, ms2);
+            e->st_launches++; e->st_deep++;
+        }
+        e->st_launches++; (spw_rest == 1 ? e->st_deep : spw_rest == 32 ? e->st_wide : e->st_group)++;
+        ingest_publish(B, 0, n);
     }
     if (kernel_ms) *kernel_ms = ms;
     { std::lock_guard<std::mutex> g(e->stat_mu); e->st_kernel_ms += ms; }
-    e->st_launches++; (spw_rest == 1 ? e->st_deep : spw_rest == 32 ? e->st_wide : e->st_group)++;
     e->st_hashed += total;
-    std::vector<Verified> good;
-    std::vector<Extent> bad;
-    if (!hash_only) good.reserve(n);
-    for (uint32_t i = 0; i < n; ++i) {
-        Digest d;
-        words_to_digest(e->ing_digests_h + 8ull * i, d.b);
-        if (digests_out) memcpy(digests_out + 32ull * i, d.b, 32);
-        const int ok = (!expect || memcmp(expect + 32ull * i, d.b, 32) == 0) ? 1 : 0;
-        if (matched_out) matched_out[i] = (uint8_t)ok;
-        if (hash_only) continue;
-        if (ok) good.push_back(Verified{d, lengths[i], ext[i]});
-        else { bad.push_back(ext[i]); e->st_mismatch++; }
-    }
-    if (!good.empty()) publish_many(e, good);
-    if (!bad.empty()) {
-        std::lock_guard<std::mutex> g(e->arena_mu);
-        for (const Extent &x : bad) e->arena.release(x.off, x.len);
-    }
     return DM_OK;
 }
 

@@ -589,25 +589,39 @@ void publish_many(dm_engine *e, const std::vector<Verified> &items)
     }
 }
 
-// Batch eviction (DM_ING_REPLACE): drop the HBM copies of these digests under one lock each way.
-void evict_many(dm_engine *e, const uint8_t *digests, uint32_t n)
+// DM_ING_REPLACE parks a cached blob instead of evicting it: the entry stays in the index, out of sight (not in HBM,
+// not in the LRU list - the state of a disk-only blob), its extent becomes the destination of the new copy.  Here the
+// verified ones come back under ONE lock; the others leave for good.  While it was parked a blob may have been
+// re-homed by a stream that carried the same digest - and then evicted again, which takes it out of the index: only
+// an entry that still maps to this very object is revived in place, anything else goes the way of a new blob.
+void unpark_many(dm_engine *e, std::vector<Parked> &verified, std::vector<Parked> &failed)
 {
-    std::vector<Extent> ext;
+    std::vector<Extent> to_free;
+    std::vector<Verified> anew;
     {
         std::lock_guard<std::mutex> g(e->mu);
-        for (uint32_t i = 0; i < n; ++i) {
-            Digest d;
-            memcpy(d.b, digests + 32ull * i, 32);
-            auto it = e->blobs.find(d);
-            if (it == e->blobs.end() || !it->second->in_hbm || it->second->readers) continue;
-            it->second->in_hbm = false;
-            lru_drop(e, it->second.get());
-            ext.insert(ext.end(), it->second->extents.begin(), it->second->extents.end());
-            it->second->extents.clear();            // under the lock (see evict_for)
-            if (!it->second->on_disk) e->blobs.erase(it);
+        constexpr size_t kAhead = 16;
+        for (size_t q = 0; q < verified.size(); ++q) {
+            if (q + kAhead < verified.size()) e->blobs.prefetch(verified[q + kAhead].b->digest);
+            Parked &k = verified[q];
+            Blob *b = k.b.get();
+            auto it = e->blobs.find(b->digest);
+            if (it == e->blobs.end() || it->second.get() != b) { anew.push_back(Verified{b->digest, b->size, k.x}); continue; }
+            if (b->in_hbm) { to_free.push_back(k.x); continue; }       // a stream re-homed it meanwhile: that copy wins
+            b->extents.assign(1, k.x);
+            b->in_hbm = true; lru_touch(e, b);
+        }
+        for (Parked &k : failed) {
+            Blob *b = k.b.get();
+            to_free.push_back(k.x);
+            if (b->in_hbm || b->on_disk) continue;
+            auto it = e->blobs.find(b->digest);
+            if (it != e->blobs.end() && it->second.get() == b) e->blobs.erase(it);
         }
     }
-    free_extents(e, ext);
+    e->st_committed += verified.size() - anew.size();
+    if (!anew.empty()) publish_many(e, anew);
+    if (!to_free.empty()) free_extents(e, to_free);
 }
 
 // ---- pump ----------------------------------------------------------------------

@@ -66,6 +66,8 @@ constexpr int kCopyStreams = 2;
 constexpr size_t kBounceBytes = 4u << 20;
 constexpr int kBounces = 48;               // 4 MiB each; readers borrow two as read-ahead windows
 constexpr int kSpillThreads = 4;           // disk-tier writers (each double-buffers two bounce buffers)
+constexpr int kIngestMaxChunks = 8;
+constexpr uint32_t kIngestChunkMin = 16384;  // jobs per chunk at least: 512 warps of the lane-per-stream kernel
 constexpr int kCompleters = 2;             // threads that compare / publish finished bodies, so the pump only launches and reaps
 constexpr int kBounceReserve = 2 * kSpillThreads + 2;          // never lent to windows: the spill thread and one-shot reads need some
 
@@ -86,9 +88,9 @@ struct DigestHash {
 
 inline void words_to_digest(const uint32_t *w, uint8_t out[32])
 {
-    for (int i = 0; i < 8; ++i) {
-        out[4 * i] = (uint8_t)(w[i] >> 24); out[4 * i + 1] = (uint8_t)(w[i] >> 16);
-        out[4 * i + 2] = (uint8_t)(w[i] >> 8); out[4 * i + 3] = (uint8_t)w[i];
+    for (int i = 0; i < 8; ++i) {                // big-endian words, FIPS 180-4 section 6.2.2
+        const uint32_t be = __builtin_bswap32(w[i]);
+        memcpy(out + 4 * i, &be, 4);
     }
 }
 
@@ -281,7 +283,7 @@ struct dm_engine {
     std::mutex slot_mu;              // state / digest slots: a lock of their own, so that opening and closing tiny bodies from
     std::vector<uint32_t> free_slots;                // many threads does not queue on the index lock `mu`
     std::atomic<uint64_t> next_id{1};
-    std::unordered_map<Digest, std::shared_ptr<Blob>, DigestHash> blobs;
+    dm::FlatIndex<Digest, std::shared_ptr<Blob>, DigestHash> blobs;      // guarded by mu; see host_util.hpp
     std::unordered_map<Digest, std::weak_ptr<Stream>, DigestHash> inflight;   // open streams by expected digest
     std::mutex reader_mu[kStripes];
     std::unordered_map<uint64_t, std::shared_ptr<Reader>> readers[kStripes];
@@ -339,6 +341,12 @@ struct dm_engine {
     uint32_t *ing_digests_h = nullptr;     // pinned
     uint32_t ing_cap = 0;
     cudaEvent_t ing_ev0{}, ing_ev1{}, ing_ev2{};
+    // dm_ingest_device over >= 2 * kIngestChunkMin lane-per-stream jobs runs as up to kIngestMaxChunks launches on
+    // streams of their own, so that the host work of chunk c + 1 (extents, job table) and of chunk c - 1 (verdicts,
+    // publication) overlaps the kernel of chunk c
+    cudaStream_t ing_streams[kIngestMaxChunks]{};
+    cudaEvent_t ing_cev_k[kIngestMaxChunks]{}, ing_cev_done[kIngestMaxChunks]{};
+    uint32_t ingest_chunks = 0;            // 0 = by the rule above; DM_INGEST_CHUNKS forces a count (tuning / tests)
 
     std::mutex pack_mu;              // tiny-body packs (see struct Pack)
     std::shared_ptr<Pack> open_pack;
@@ -417,8 +425,9 @@ std::string blob_path(const dm_engine *e, const uint8_t d[32]);
 std::shared_ptr<Blob> publish(dm_engine *e, const Digest &d, uint64_t size, std::vector<Extent> &ext,
                               std::vector<std::pair<std::string, std::string>> *meta = nullptr);
 struct Verified { Digest d; uint64_t size; Extent x; };      // one blob of a device-resident batch, hashed and matched
+struct Parked { std::shared_ptr<Blob> b; Extent x; };        // a cached blob taken out of sight while its extent is rewritten
 void publish_many(dm_engine *e, const std::vector<Verified> &items);
-void evict_many(dm_engine *e, const uint8_t *digests, uint32_t n);
+void unpark_many(dm_engine *e, std::vector<Parked> &verified, std::vector<Parked> &failed);
 void wait_follow_reads(Stream *s, std::unique_lock<std::mutex> &g);
 void complete_stream(dm_engine *e, const std::shared_ptr<Stream> &sp, const uint32_t *words);
 void completer_main(dm_engine *e);

@@ -243,7 +243,8 @@ int dm_cache_alias_get(dm_engine *e, const char *key, uint8_t digest_out[32]);
  * kernel_ms (optional) = CUDA-event time of the hash launches on the
  * engine's own stream.  flags: DM_ING_* below. */
 #define DM_ING_HASH_ONLY   0x1u   /* do not copy into the CAS (1 B/B of traffic instead of 2) */
-#define DM_ING_REPLACE     0x2u   /* evict an existing blob with the same digest first (benchmarks) */
+#define DM_ING_REPLACE     0x2u   /* re-ingest: a cached blob with an expected digest is taken out of sight for the
+                                   * call and - when it has no reader - its extent is rewritten in place */
 #define DM_ING_FORCE_WIDE  0x4u   /* kernel selection override: lane-per-stream */
 #define DM_ING_FORCE_DEEP  0x8u   /* kernel selection override: warp-per-stream */
 #define DM_ING_SPW_SHIFT   8      /* kernel selection override: (log2(streams per warp) + 1) << 8, */

@@ -225,16 +225,20 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
             CHECK(rc == DM_OK);
             CHECK(matched == 1 && memcmp(got, b.digest, 32) == 0);
         } else if (op == 12 && !vo) {                       // a ragged batch already "in HBM": one launch
-            const uint32_t nb = 1 + (uint32_t)(rng() % 24);
+            // half of the batches come from a small set that is ingested again and again (REPLACE then finds the previous
+            // copies cached and rewrites their extents in place), the others are new every time
+            const bool again = rng() & 1;
+            const uint64_t first = again ? 9000 + 64 * (rng() % 12) : 20000 + rng() % 100000;
+            std::mt19937_64 lrng(again ? first : rng());
+            const uint32_t nb = 1 + (uint32_t)(lrng() % 24);
             std::vector<uint64_t> off(nb), len(nb);
             uint64_t pos = 0;
             for (uint32_t i = 0; i < nb; ++i) {
                 off[i] = pos;
-                len[i] = (rng() % 6 == 0) ? 0 : 16 * (rng() % 3000) + (rng() % 3 == 0 ? rng() % 16 : 0);
+                len[i] = (lrng() % 6 == 0) ? 0 : 16 * (lrng() % 3000) + (lrng() % 3 == 0 ? lrng() % 16 : 0);
                 pos += (len[i] + 15) / 16 * 16;
             }
             std::vector<uint8_t> dev(pos + 16);                      // the rig's device memory is host memory
-            const uint64_t first = 9000 + rng() % 100000;
             rc = dm_synth_fill_device_many(e, 0xDE40DE1, first, dev.data(), off.data(), len.data(), nb);
             if (tolerate(rc)) continue;
             CHECK(rc == DM_OK);
@@ -580,6 +584,85 @@ static void lost_bytes_are_sticky()
     dm_engine_destroy(e);
 }
 
+// dm_ingest_device over blobs that are already cached (DM_ING_REPLACE): the previous copies are parked and their extents
+// written again in place, in chunks on streams of their own when the batch is large (forced here with
+// DM_INGEST_CHUNKS).  The arena has room for ONE copy of the batch plus a little: evicting and re-allocating out of
+// order, or leaking a parked extent, shows as DM_ENOMEM or as a changed hbm_cas_used.
+static void bulk_replace_rewrites_cached_blobs_in_place()
+{
+    setenv("DM_INGEST_CHUNKS", "3", 1);
+    const uint32_t n = 1500;
+    std::vector<uint64_t> off(n), len(n);
+    std::mt19937_64 rng(77);
+    uint64_t pos = 0, arena = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        off[i] = pos;
+        len[i] = i % 97 == 0 ? 0 : 16 * (rng() % 200) + (i % 5 == 0 ? rng() % 16 : 0);      // ragged, some empty
+        pos += (len[i] + 15) / 16 * 16;
+        arena += (std::max<uint64_t>(len[i], 1) + 255) / 256 * 256;
+    }
+    dm_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = sizeof cfg;
+    cfg.hbm_cas_bytes = arena + (64u << 10); cfg.ring_bytes = 1u << 20; cfg.slab_bytes = 64u << 10; cfg.max_streams = 64;
+    dm_engine *e = nullptr;
+    CHECK(dm_engine_create(&cfg, &e) == DM_OK);
+    unsetenv("DM_INGEST_CHUNKS");
+    std::vector<uint8_t> dev(pos + 16);
+    CHECK(dm_synth_fill_device_many(e, 0xDE40DE1, 70000, dev.data(), off.data(), len.data(), n) == DM_OK);
+    std::vector<uint8_t> want(32 * n), digs(32 * n), mat(n);
+    for (uint32_t i = 0; i < n; ++i) dmo_sha256(dev.data() + off[i], len[i], &want[32 * i]);
+    auto check_cached = [&](uint32_t i, bool present) {
+        uint64_t rid = 0, size = 0;
+        const int rc = dm_cache_open(e, &want[32 * i], &rid, &size);
+        if (!present) { CHECK(rc == DM_ENOENT); return; }
+        CHECK(rc == DM_OK && size == len[i]);
+        void *ptrs[4];
+        uint64_t lens[4];
+        const int ne = dm_cache_device_extents(e, rid, ptrs, lens, 4);
+        CHECK(ne == 1 && lens[0] == len[i] && (len[i] == 0 || memcmp(ptrs[0], dev.data() + off[i], len[i]) == 0));
+        CHECK(dm_cache_close(e, rid) == DM_OK);
+    };
+    dm_stats st0, st;
+    for (int round = 0; round < 4; ++round) {
+        // round 0: everything is new; 1: lane per stream, chunked; 2: 8 streams per warp (one launch, jobs sorted by
+        // length, so positions differ from the caller's indices); 3: the kernel the count picks
+        const uint32_t shape = round == 1 ? 6u << DM_ING_SPW_SHIFT : round == 2 ? 4u << DM_ING_SPW_SHIFT : 0;
+        uint64_t pinned = 0, psize = 0;
+        if (round == 2) CHECK(dm_cache_open(e, &want[32 * 11], &pinned, &psize) == DM_OK);      // a blob with a reader stays where it is
+        std::fill(mat.begin(), mat.end(), 7);
+        CHECK(dm_ingest_device(e, dev.data(), off.data(), len.data(), n, want.data(), digs.data(), mat.data(), DM_ING_REPLACE | shape, nullptr) == DM_OK);
+        CHECK(memcmp(digs.data(), want.data(), 32 * n) == 0);
+        for (uint32_t i = 0; i < n; ++i) CHECK(mat[i] == 1);
+        if (pinned) CHECK(dm_cache_close(e, pinned) == DM_OK);
+        CHECK(dm_engine_stats(e, &st) == DM_OK);
+        if (round == 0) st0 = st;
+        CHECK(st.hbm_cas_used == st0.hbm_cas_used);
+        if (round == 1) CHECK(st.kernel_launches - st0.kernel_launches == 3 && st.launches_wide == 3);
+        for (uint32_t i = 0; i < n; i += 37) check_cached(i, true);
+        check_cached(11, true);
+        check_cached(n - 1, true);
+    }
+    // the bytes of one blob change under its cached copy: the re-ingest reports the mismatch and that blob is gone
+    const uint32_t m = 501;
+    CHECK(len[m] > 0);
+    dev[off[m]] ^= 0x40;
+    CHECK(dm_ingest_device(e, dev.data(), off.data(), len.data(), n, want.data(), digs.data(), mat.data(), DM_ING_REPLACE | (6u << DM_ING_SPW_SHIFT), nullptr) == DM_OK);
+    for (uint32_t i = 0; i < n; ++i) CHECK(mat[i] == (i == m ? 0 : 1));
+    check_cached(m, false);
+    check_cached(m - 1, true);
+    check_cached(m + 1, true);
+    CHECK(dm_engine_stats(e, &st) == DM_OK);
+    CHECK(st.hbm_cas_used == st0.hbm_cas_used - (len[m] + 255) / 256 * 256 && st.blobs_mismatched == 1);
+    dmo_sha256(dev.data() + off[m], len[m], &want[32 * m]);                  // what is there now goes in as a new blob
+    CHECK(dm_ingest_device(e, dev.data(), off.data(), len.data(), n, want.data(), digs.data(), mat.data(), DM_ING_REPLACE, nullptr) == DM_OK);
+    for (uint32_t i = 0; i < n; ++i) CHECK(mat[i] == 1);
+    check_cached(m, true);
+    CHECK(dm_engine_stats(e, &st) == DM_OK);
+    CHECK(st.hbm_cas_used == st0.hbm_cas_used && st.open_readers == 0);
+    dm_engine_destroy(e);
+}
+
 // Shutdown with transfers in flight: the proxy is stopped while bodies are half way and hits are being served.
 // Destroy must not hang, crash or touch freed memory (ASan), whatever state the streams and readers are in.
 static void destroy_with_open_handles(const char *cas_dir)
@@ -727,6 +810,7 @@ int main(int argc, char **argv)
     if (!failures.load() && !g_inject) driver_phase(verify_only);
     if (!failures.load() && !verify_only && !g_inject) destroy_with_open_handles(cas_dir);
     if (!failures.load() && !verify_only && !g_inject && !cas_dir) lost_bytes_are_sticky();
+    if (!failures.load() && !verify_only && !g_inject && !cas_dir) bulk_replace_rewrites_cached_blobs_in_place();
     if (failures.load() || !clean) { printf("ENGINE SOAK FAILED\n"); return 1; }
     printf("ENGINE SOAK OK\n");
     return 0;

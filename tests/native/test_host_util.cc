@@ -4,7 +4,9 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <random>
+#include <unordered_map>
 #include <vector>
 
 #define CHECK(c) do { if (!(c)) { fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); exit(1); } } while (0)
@@ -110,8 +112,66 @@ static void interval_model_test(uint64_t seed)
     CHECK(m.size() == 1 && m[0] == 20);
 }
 
+// FlatIndex against std::unordered_map under random insert / find / erase, with a hash that throws most keys into a
+// few probe runs (long clusters, wrap-around at the end of the table) and with a well-spread one; values are
+// shared_ptrs so that a slot dropped or moved wrongly shows up as a wrong use count.
+struct Key32 { uint8_t b[32]; bool operator==(const Key32 &o) const { return memcmp(b, o.b, 32) == 0; } };
+struct SpreadHash { size_t operator()(const Key32 &k) const { uint64_t v; memcpy(&v, k.b, 8); return (size_t)v; } };
+struct ClusterHash { size_t operator()(const Key32 &k) const { uint64_t v; memcpy(&v, k.b, 8); return (size_t)(v % 7 == 0 ? 0 : 1016 + v % 13); } };
+struct StdHash { size_t operator()(const Key32 &k) const { uint64_t v; memcpy(&v, k.b + 8, 8); return (size_t)v; } };
+
+template <class H>
+static void flat_index_model_test(uint64_t seed, int steps, int keyspace)
+{
+    dm::FlatIndex<Key32, std::shared_ptr<int>, H> idx;
+    std::unordered_map<Key32, std::shared_ptr<int>, StdHash> model;
+    std::mt19937_64 rng(seed);
+    auto key_of = [&](uint64_t k) { Key32 x; std::mt19937_64 g(k * 7919 + 1); for (int i = 0; i < 32; i += 8) { const uint64_t w = g(); memcpy(x.b + i, &w, 8); } return x; };
+    CHECK(idx.find(key_of(1)) == idx.end() && idx.erase(key_of(1)) == 0);
+    for (int step = 0; step < steps; ++step) {
+        const Key32 k = key_of(rng() % keyspace);
+        const int op = (int)(rng() % 8);
+        auto mit = model.find(k);
+        if (op < 3) {
+            auto v = std::make_shared<int>(step);
+            auto r = idx.emplace(k, v);
+            CHECK(r.second == (mit == model.end()));
+            if (r.second) model.emplace(k, v);
+            CHECK(*r.first->second == *model.find(k)->second && r.first->first == k);
+        } else if (op < 5) {
+            auto it = idx.find(k);
+            CHECK((it == idx.end()) == (mit == model.end()));
+            if (it != idx.end()) CHECK(it->second == mit->second && it->second.use_count() == 2);
+            idx.prefetch(k);
+        } else if (op == 5) {
+            auto &slot = idx[k];                               // default-constructs when absent, like the map
+            if (mit == model.end()) { CHECK(!slot); slot = std::make_shared<int>(-step); model[k] = slot; }
+            else CHECK(slot == mit->second);
+        } else if (op == 6) {
+            auto it = idx.find(k);
+            if (it != idx.end()) { idx.erase(it); model.erase(k); }
+        } else {
+            CHECK(idx.erase(k) == model.erase(k));
+        }
+        CHECK(idx.size() == model.size());
+        if (step % 997 == 0 || step == steps - 1) {            // whole-table agreement
+            size_t seen = 0;
+            idx.for_each([&](const typename decltype(idx)::Slot &s) { ++seen; auto m = model.find(s.first); CHECK(m != model.end() && m->second == s.second); });
+            CHECK(seen == model.size());
+            for (auto &kv : model) { auto it = idx.find(kv.first); CHECK(it != idx.end() && it->second == kv.second && kv.second.use_count() == 2); }
+            CHECK(idx.capacity() == 0 || idx.size() * 2 <= idx.capacity());
+        }
+    }
+    if (keyspace <= 4096) {
+        idx.reserve(100000);                                   // growth keeps every entry
+        for (auto &kv : model) { auto it = idx.find(kv.first); CHECK(it != idx.end() && it->second == kv.second); }
+    }
+}
+
 int main()
 {
+    for (uint64_t s = 1; s <= 3; ++s) { flat_index_model_test<SpreadHash>(s, 60000, 3000); flat_index_model_test<ClusterHash>(s, 40000, 700); }
+    flat_index_model_test<SpreadHash>(9, 200000, 40000);
     for (uint64_t s = 1; s <= 4; ++s) arena_model_test(s);
     for (uint64_t s = 1; s <= 4; ++s) interval_model_test(s);
     printf("host_util ok\n");
