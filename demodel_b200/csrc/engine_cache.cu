@@ -688,7 +688,7 @@ static int ingest_device_impl(dm_engine *e, const void *dev_base, const uint64_t
             }
             if (err != cudaSuccess) break;
         }
-        while (rc == DM_OK && err == cudaSuccess && reaped < launched) reap();
+        while (err == cudaSuccess && reaped < launched) reap();     // also when a later chunk found no room: these are done
         if (rc != DM_OK || err != cudaSuccess) {
             for (uint32_t c = 0; c < launched; ++c) cudaStreamSynchronize(e->ing_streams[c]);
             ingest_unwind(B);
