@@ -36,4 +36,4 @@ with demodel_b200.Engine(device=0, hbm_cas_bytes=(n * size * 2) + (64 << 20), ri
         best = min(ts[2:])
         print(f"{phase}: {n} blobs, best of {steps}: {best * 1e3:7.2f} ms per call = {best / n * 1e9:6.1f} ns per blob")
     st = eng.stats()
-    print("blobs resident:", st.get("blobs"), "launches:", st["kernel_launches"])
+    print(f"launches: {st['kernel_launches']} ({st['launches_wide']} lane-per-stream), blobs committed: {st['blobs_committed']}")

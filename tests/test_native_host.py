@@ -171,6 +171,11 @@ def test_python_mirror_gpu_test_logic_and_bench_flow_over_the_fake_runtime(tmp_p
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
     assert line["warmup"] >= 3 and line["gpu_launches"] > 0 and line["config"]["workload"] == "tiny"
     assert line["e2e"]["h2d_bytes_per_step"] == line["config"]["bytes_per_gpu_per_step"]
+    # the host-cost probes (engine over null kernels) must keep working: they are how host-side work on the bulk and
+    # tiny-body paths is measured without a GPU.  40 000 blobs: enough for the chunked-launch rule to apply.
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "native", "bulk_cost_probe.py"), str(lib), "40000", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert out.returncode == 0 and out.stdout.count("ns per blob") == 2, (out.stdout + out.stderr)[-2000:]
 
 
 def test_sass_timing_model_reproduces_the_measured_deep_kernel(tmp_path):
