@@ -34,6 +34,7 @@ with demodel_b200.Engine(device=0, hbm_cas_bytes=(n * size * 2) + (64 << 20), ri
             ts.append(time.perf_counter() - t0)
             assert m.all()
         best = min(ts[2:])
-        print(f"{phase}: {n} blobs, best of {steps}: {best * 1e3:7.2f} ms per call = {best / n * 1e9:6.1f} ns per blob")
+        print(f"{phase}: {n} blobs, best of {steps}: {best * 1e3:7.2f} ms per call = {best / n * 1e9:6.1f} ns per blob"
+              f"  (first call, everything new: {ts[0] * 1e3:.2f} ms)")
     st = eng.stats()
     print(f"launches: {st['kernel_launches']} ({st['launches_wide']} lane-per-stream), blobs committed: {st['blobs_committed']}")
