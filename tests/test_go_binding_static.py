@@ -62,7 +62,7 @@ def _header():
     consts = set(re.findall(r"#define\s+(DM_\w+)", h)) | set(re.findall(r"\b(DM_[A-Z0-9_]+)\s*=", h))
     types = set(re.findall(r"\}\s*(dm_\w+)\s*;", h)) | set(re.findall(r"typedef\s+struct\s+\w+\s+(dm_\w+)\s*;", h))
     fields = {}
-    for m in re.finditer(r"typedef\s+struct\s*\w*\s*\{(.*?)\}\s*(dm_\w+)\s*;", h, flags=re.S):
+    for m in re.finditer(r"typedef\s+struct\s*\w*\s*\{([^{}]*)\}\s*(dm_\w+)\s*;", h):
         fields[m.group(2)] = set(re.findall(r"(\w+)\s*(?:\[[^\]]*\])?\s*;", m.group(1)))
     return funcs, consts, types, fields
 
@@ -104,3 +104,21 @@ def test_every_exported_entry_point_is_declared_once():
     h = _strip_comments(open(os.path.join(ROOT, "include", "demodel_b200.h")).read())
     names = re.findall(r"^\s*(?:const\s+char\s*\*|int|void|uint32_t|size_t)\s*\**\s*(dm_\w+)\s*\(", h, flags=re.M)
     assert len(names) == len(set(names)), sorted(n for n in names if names.count(n) > 1)
+
+
+def test_ctypes_table_matches_the_header():
+    """The Python mirror's signature table (demodel_b200/_lib.py) against the same parse of the header: same entry
+    points, same number of arguments each - a mismatch there corrupts the stack silently instead of failing."""
+    from demodel_b200 import _lib
+    funcs, _, _, fields = _header()
+    assert set(_lib.SIGNATURES) == set(funcs), (sorted(set(funcs) - set(_lib.SIGNATURES)), sorted(set(_lib.SIGNATURES) - set(funcs)))
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert len(argtypes) == funcs[name], f"{name}: {len(argtypes)} ctypes arguments, {funcs[name]} in the header"
+    for cls, typ in ((_lib.DmStats, "dm_stats"), (_lib.DmLayer, "dm_layer"), (_lib.DmCheckpoint, "dm_checkpoint"), (_lib.DmConfig, "dm_config")):
+        assert [f[0] for f in cls._fields_] == [f for f in _ordered_fields(typ)], typ
+
+
+def _ordered_fields(typ):
+    h = _strip_comments(open(os.path.join(ROOT, "include", "demodel_b200.h")).read())
+    body = re.search(r"typedef\s+struct\s*\w*\s*\{([^{}]*)\}\s*" + typ + r"\s*;", h).group(1)
+    return re.findall(r"(\w+)\s*(?:\[[^\]]*\])?\s*;", body)
