@@ -122,3 +122,15 @@ def _ordered_fields(typ):
     h = _strip_comments(open(os.path.join(ROOT, "include", "demodel_b200.h")).read())
     body = re.search(r"typedef\s+struct\s*\w*\s*\{([^{}]*)\}\s*" + typ + r"\s*;", h).group(1)
     return re.findall(r"(\w+)\s*(?:\[[^\]]*\])?\s*;", body)
+
+
+def test_documents_name_only_entry_points_that_exist():
+    """INTEGRATION.md is what a maintainer of the Go proxy reads: every dm_* name in it (and in DESIGN.md / README.md)
+    must be an entry point, a type, or a prefix family (`dm_cache_alias_*`) of the header."""
+    funcs, _, types, _ = _header()
+    known_tools = {"dm_sha256sum"}                                    # tools/dm_sha256sum.py
+    for doc in ("INTEGRATION.md", "DESIGN.md", "README.md"):
+        text = open(os.path.join(ROOT, doc)).read()
+        for name in set(re.findall(r"\b(dm_[a-z0-9_]+)\b", text)):
+            ok = name in funcs or name in types or name in known_tools or any(f.startswith(name.rstrip("_")) for f in funcs)
+            assert ok, f"{doc} mentions {name}, which include/demodel_b200.h does not declare"
