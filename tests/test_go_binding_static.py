@@ -134,3 +134,20 @@ def test_documents_name_only_entry_points_that_exist():
         for name in set(re.findall(r"\b(dm_[a-z0-9_]+)\b", text)):
             ok = name in funcs or name in types or name in known_tools or any(f.startswith(name.rstrip("_")) for f in funcs)
             assert ok, f"{doc} mentions {name}, which include/demodel_b200.h does not declare"
+
+
+def test_go_source_is_at_least_well_bracketed():
+    """No compiler here: the cheapest syntax check there is.  Brackets balance outside strings, runes and comments, and
+    the cgo preamble includes the header this repository ships."""
+    go = open(os.path.join(ROOT, "go", "demodel_b200.go")).read()
+    assert '#include "demodel_b200.h"' in go and re.search(r'^import\s+"C"', go, flags=re.M)
+    code = re.sub(r'"(?:[^"\\\n]|\\.)*"|`[^`]*`|\'(?:[^\'\\\n]|\\.)+\'', '""', go)
+    code = _strip_comments(code)
+    stack = []
+    pairs = {")": "(", "]": "[", "}": "{"}
+    for ch in code:
+        if ch in "([{":
+            stack.append(ch)
+        elif ch in ")]}":
+            assert stack and stack.pop() == pairs[ch], "unbalanced " + ch
+    assert not stack
