@@ -87,6 +87,30 @@ def main():
     st = eng.stats()
     leak = not (st["open_streams"] == 0 and st["open_readers"] == 0 and st["ring_slabs_free"] == st["ring_slabs_total"])
     eng.close()
+    # __graft_entry__.smoke() is what the driver runs first on the GPU box: its control flow, too, is worth a CPU pass
+    import types
+    import numpy as np
+    from fake_device import _Dev
+    stub = types.ModuleType("torch")
+    stub.uint8 = np.uint8
+    stub.cuda = types.SimpleNamespace(is_available=lambda: True)
+    stub.zeros = lambda n, dtype=None, device=None: _Dev(np.zeros(n, dtype=np.uint8))
+    had = sys.modules.get("torch")
+    sys.modules["torch"] = stub
+    try:
+        import __graft_entry__
+        __graft_entry__.smoke()
+        print("ok    __graft_entry__.smoke() over the fake runtime", flush=True)
+    except BaseException:
+        failed.append("smoke")
+        print("FAIL  __graft_entry__.smoke()", flush=True)
+        traceback.print_exc()
+    finally:
+        if had is not None:
+            sys.modules["torch"] = had
+        else:
+            del sys.modules["torch"]
+    ran += 1
     print(f"MIRROR TESTS: {ran} ran, {len(failed)} failed, leak={int(leak)}")
     return 1 if failed or leak or ran < 10 else 0
 
