@@ -84,7 +84,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
         uint8_t got[32];
         int matched = -1, rc;
         uint64_t id = 0;
-        const int op = (int)(rng() % 20);
+        const int op = (int)(rng() % 21);
         ops++;
         where[tid & 63] = op * 1000 + (int)(n >> 10);
         if (op <= 1) {                                               // sequential, random piece size
@@ -457,6 +457,35 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
             else { CHECK(rc == DM_ESTATE || rc == DM_EINVAL || tolerate(rc)); if (rc == DM_ENOMEM || rc == DM_ECUDA) dm_stream_abort(e, id); }
             if (op == 19 && rc2 == DM_OK) CHECK(m2 == 1 && memcmp(got2, b.digest, 32) == 0);
             if (rc2 != DM_OK) CHECK(rc2 == DM_ESTATE || rc2 == DM_EINVAL || tolerate(rc2));
+        } else if (op == 20 && !vo) {                                // a STREAM carries a blob of the re-ingested sets (op 12):
+            // while a batch has that blob parked, publication of this body re-homes the entry and the batch must yield
+            const uint64_t first = 9000 + 64 * (rng() % 12);
+            std::mt19937_64 lrng(first);
+            const uint32_t nb = 1 + (uint32_t)(lrng() % 24);
+            std::vector<uint64_t> len(nb);
+            for (uint32_t i = 0; i < nb; ++i) len[i] = (lrng() % 6 == 0) ? 0 : 16 * (lrng() % 3000) + (lrng() % 3 == 0 ? lrng() % 16 : 0);
+            const uint32_t i = (uint32_t)(rng() % nb);
+            std::vector<uint8_t> mine(len[i]);
+            dm_synth_fill_host(0xDE40DE1, first + i, 0, mine.data(), len[i]);
+            uint8_t md[32];
+            dmo_sha256(mine.data(), len[i], md);
+            rc = dm_stream_open(e, md, len[i], &id);
+            if (tolerate(rc)) continue;
+            CHECK(rc == DM_OK);
+            rc = dm_stream_write(e, id, mine.data(), len[i]);
+            if (rc != DM_OK) { CHECK(tolerate(rc)); dm_stream_abort(e, id); continue; }
+            rc = finish_or_skip(e, id, false, got, &matched);
+            if (rc == 1) continue;
+            CHECK(rc == DM_OK && matched == 1 && memcmp(got, md, 32) == 0);
+            uint64_t rid = 0, size = 0;
+            if (dm_cache_open(e, md, &rid, &size) == DM_OK) {        // (it may be parked by a batch right now: a miss is fine)
+                CHECK(size == len[i]);
+                size_t nread = 0;
+                rc = dm_cache_read(e, rid, 0, scratch.data(), std::min<size_t>(len[i], scratch.size()), &nread);
+                if (rc == DM_OK) CHECK(nread == std::min<size_t>(len[i], scratch.size()) && memcmp(scratch.data(), mine.data(), nread) == 0);
+                else CHECK(tolerate(rc));
+                CHECK(dm_cache_close(e, rid) == DM_OK);
+            }
         } else if (op == 11) {                                       // metadata + stats are always safe to call
             dm_stats st;
             CHECK(dm_engine_stats(e, &st) == DM_OK);
