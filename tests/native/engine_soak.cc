@@ -465,7 +465,7 @@ static void worker(dm_engine *e, int tid, double seconds, bool verify_only)
             std::vector<uint64_t> len(nb);
             for (uint32_t i = 0; i < nb; ++i) len[i] = (lrng() % 6 == 0) ? 0 : 16 * (lrng() % 3000) + (lrng() % 3 == 0 ? lrng() % 16 : 0);
             const uint32_t i = (uint32_t)(rng() % nb);
-            std::vector<uint8_t> mine(len[i]);
+            std::vector<uint8_t> mine(len[i] + 1);                   // (+1: data() of an empty vector may be null)
             dm_synth_fill_host(0xDE40DE1, first + i, 0, mine.data(), len[i]);
             uint8_t md[32];
             dmo_sha256(mine.data(), len[i], md);
