@@ -241,7 +241,10 @@ int dm_cache_alias_get(dm_engine *e, const char *key, uint8_t digest_out[32]);
  * state and writes the byte into the blob's CAS extent.  digests_out gets
  * n*32 bytes; matched_out (n bytes, optional) the per-blob verdicts.
  * kernel_ms (optional) = CUDA-event time of the hash launches on the
- * engine's own stream.  flags: DM_ING_* below. */
+ * engine's own stream(s): a batch of 32 768 or more small blobs goes out as
+ * up to 8 launches on as many streams, so that extents, verdicts and index
+ * updates of one part overlap the kernel of another; kernel_ms then runs
+ * from the first launch to the end of the last.  flags: DM_ING_* below. */
 #define DM_ING_HASH_ONLY   0x1u   /* do not copy into the CAS (1 B/B of traffic instead of 2) */
 #define DM_ING_REPLACE     0x2u   /* re-ingest: a cached blob with an expected digest is taken out of sight for the
                                    * call and - when it has no reader - its extent is rewritten in place */
